@@ -1,0 +1,769 @@
+// api.cu — the C-ABI of include/ftsb.h: handle management, parameter upload, kernel dispatch.
+// No CPU fallback: every entry point that computes needs a CUDA device and fails loudly without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ftsb.h"
+#include "compile.h"
+#include "engine.cuh"
+
+using namespace ftsb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(bytes, (size_t)256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct ftsb_circuit {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    Compiled comp;
+    DevBuf ibuf;
+    DevProg prog{};
+    long long batch = 0;
+    DevBuf vals, fn, tmp_in, work, counters, scratch;
+    // staging of outputs when the caller's buffers are on the host
+    DevBuf o_x, o_it, o_status, o_done, o_t, o_nrec, o_xf, i_start, i_stop, i_step;
+    std::string err;
+    std::string variant = "none";
+    long long launches = 0;
+    int skip_refactor = 1;
+    int force_cta = 0;
+};
+
+#define FTSB_CUDA(c, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (c)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+            return FTSB_E_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+namespace {
+
+int fail(ftsb_circuit *c, int code, const std::string &msg)
+{
+    if (c)
+        c->err = msg;
+    else
+        g_last_error = msg;
+    return code;
+}
+
+Gather dev_gather(const int *base, const GatherOff &o)
+{
+    Gather g;
+    g.dst = base + o.dst;
+    g.ptr = base + o.ptr;
+    g.con = base + o.con;
+    g.n_dst = o.n_dst;
+    g.n_con = o.n_con;
+    return g;
+}
+
+ModeProg dev_mode(const int *base, const ModeOff &o)
+{
+    ModeProg m;
+    m.n = o.n;
+    m.nv = o.nv;
+    m.ni = o.ni;
+    m.n_nl = o.n_nl;
+    m.n_gfun = o.n_gfun;
+    m.pad = 0;
+    m.cls = base + o.cls;
+    m.nl = base + o.nl;
+    m.A_lin = dev_gather(base, o.A_lin);
+    m.A_dyn = dev_gather(base, o.A_dyn);
+    m.J_nl = dev_gather(base, o.J_nl);
+    m.b_all = dev_gather(base, o.b_all);
+    m.r_nl = dev_gather(base, o.r_nl);
+    m.f_nl = dev_gather(base, o.f_nl);
+    return m;
+}
+
+// ---- kernel variants -------------------------------------------------------------------------------------
+typedef void (*KernelFn)(const RunArgs);
+
+template <int AN>
+KernelFn subwarp_kernel(int g)
+{
+    switch (g) {
+    case 4:
+        return (KernelFn)k_subwarp<4, AN>;
+    case 8:
+        return (KernelFn)k_subwarp<8, AN>;
+    case 16:
+        return (KernelFn)k_subwarp<16, AN>;
+    default:
+        return (KernelFn)k_subwarp<32, AN>;
+    }
+}
+
+KernelFn pick_kernel(int an, int g /*0 = cta*/)
+{
+    if (g == 0) return an == AN_OP ? (KernelFn)k_cta<AN_OP> : an == AN_DC ? (KernelFn)k_cta<AN_DC> : (KernelFn)k_cta<AN_TRAN>;
+    return an == AN_OP ? subwarp_kernel<AN_OP>(g) : an == AN_DC ? subwarp_kernel<AN_DC>(g) : subwarp_kernel<AN_TRAN>(g);
+}
+
+struct LaunchPlan {
+    int g = 0; // sub-warp group size, 0 = CTA team
+    int block = 128;
+    int grid = 1;
+    size_t smem = 0;
+    Layout lay;
+    size_t scratch_bytes = 0;
+};
+
+int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
+{
+    const int n = std::max(c->comp.n_start, 1);
+    Layout L = c->comp.lay;
+    const size_t vec_bytes = (size_t)L.doubles * 8;
+    const size_t mat_bytes = (size_t)2 * L.mat_doubles * 8;
+    const size_t int_bytes = (size_t)L.ints * 4;
+    int g = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 0;
+    if (c->force_cta) g = 0;
+    if (g) {
+        size_t per = (vec_bytes + mat_bytes + int_bytes + 15) & ~(size_t)15;
+        int teams = 128 / g;
+        if (per * teams > c->smem_optin) g = 0; // too many slots for a sub-warp block: use a CTA
+        else {
+            L.mat_in_smem = 1;
+            L.bytes = (int)per;
+            pl.g = g;
+            pl.block = 128;
+            pl.smem = per * teams;
+            pl.lay = L;
+            pl.scratch_bytes = 0;
+            KernelFn fn = pick_kernel(an, g);
+            cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            if (e != cudaSuccess) return fail(c, FTSB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+            int occ = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, pl.block, pl.smem);
+            if (e != cudaSuccess || occ < 1) return fail(c, FTSB_E_CUDA, "occupancy query failed for the sub-warp kernel");
+            long long need = (batch + teams - 1) / teams;
+            pl.grid = (int)std::max(1LL, std::min(need, (long long)occ * c->sm_count));
+            c->variant = "warp" + std::to_string(g);
+            return 0;
+        }
+    }
+    // CTA team: one thread per row
+    int block = ((n + 31) / 32) * 32;
+    if (block < 64) block = 64;
+    if (block > 1024) return fail(c, FTSB_E_UNSUPPORTED, "circuits with more than 1024 unknowns are not supported yet");
+    size_t base = 96 * 8 + vec_bytes + int_bytes;
+    L.mat_in_smem = (base + mat_bytes <= c->smem_optin) ? 1 : 0;
+    if (base > c->smem_optin) return fail(c, FTSB_E_UNSUPPORTED, "per-instance vectors exceed shared memory");
+    pl.g = 0;
+    pl.block = block;
+    pl.smem = (base + (L.mat_in_smem ? mat_bytes : 0) + 15) & ~(size_t)15;
+    L.bytes = (int)pl.smem;
+    pl.lay = L;
+    KernelFn fn = pick_kernel(an, 0);
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return fail(c, FTSB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, pl.block, pl.smem);
+    if (e != cudaSuccess || occ < 1) return fail(c, FTSB_E_CUDA, "occupancy query failed for the CTA kernel");
+    pl.grid = (int)std::max(1LL, std::min(batch, (long long)occ * c->sm_count));
+    pl.scratch_bytes = L.mat_in_smem ? 0 : (size_t)pl.grid * mat_bytes;
+    c->variant = std::string("cta") + std::to_string(block) + (L.mat_in_smem ? "" : "g");
+    return 0;
+}
+
+int launch(ftsb_circuit *c, int an, RunArgs &a)
+{
+    LaunchPlan pl;
+    int rc = plan_launch(c, an, a.batch, pl);
+    if (rc) return rc;
+    if (pl.scratch_bytes) FTSB_CUDA(c, c->scratch.ensure(pl.scratch_bytes));
+    a.prog = c->prog;
+    a.prog.lay = pl.lay;
+    a.scratch = (double *)c->scratch.p;
+    a.work = (unsigned long long *)c->work.p;
+    a.counters = (unsigned long long *)c->counters.p;
+    a.skip_refactor = c->skip_refactor;
+    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+    FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
+    KernelFn fn = pick_kernel(an, pl.g);
+    void *args[] = {&a};
+    FTSB_CUDA(c, cudaLaunchKernel((const void *)fn, dim3(pl.grid), dim3(pl.block), args, pl.smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
+__global__ void k_transpose(const double *__restrict__ in, double *__restrict__ out, long long rows, long long cols)
+{
+    // in[rows][cols] -> out[cols][rows]
+    __shared__ double tile[32][33];
+    long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long r = r0 + j, cc = c0 + threadIdx.x;
+        if (r < rows && cc < cols) tile[j][threadIdx.x] = in[r * cols + cc];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        long long cc = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && cc < cols) out[cc * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+int check_ready(ftsb_circuit *c)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    if (c->batch <= 0) return fail(c, FTSB_E_STATE, "ftsb_set_params must be called before a run");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, FTSB_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ftsb_abi_version(void) { return FTSB_ABI_VERSION; }
+
+int ftsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *ftsb_last_error(const ftsb_circuit *c) { return c ? c->err.c_str() : g_last_error.c_str(); }
+
+int ftsb_compile(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t n_start, const int32_t *row_class,
+                 int device, ftsb_circuit **out)
+{
+    if (!out) return fail(nullptr, FTSB_E_ARG, "ftsb_compile: out is NULL");
+    *out = nullptr;
+    if (n_elems > 0 && !elems) return fail(nullptr, FTSB_E_ARG, "ftsb_compile: elems is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, FTSB_E_CUDA,
+                    std::string("ftsb_compile: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                        "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, FTSB_E_ARG, "ftsb_compile: bad device ordinal");
+    static_assert(sizeof(ftsb_elem) == sizeof(ElemDesc), "ABI element layout");
+    ftsb_circuit *c = new ftsb_circuit();
+    c->device = device;
+    std::string err;
+    if (!compile_circuit(reinterpret_cast<const ElemDesc *>(elems), n_elems, n_run, n_start, row_class, c->comp, err)) {
+        delete c;
+        return fail(nullptr, FTSB_E_ARG, err);
+    }
+    auto bail = [&](const std::string &m, int code) {
+        g_last_error = m;
+        ftsb_destroy(c);
+        return code;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    c->own_stream = true;
+    const std::vector<int> &ib = c->comp.ints();
+    if ((e = c->ibuf.ensure(std::max<size_t>(ib.size(), 2) * 4)) != cudaSuccess)
+        return bail(std::string("cudaMalloc: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    if (!ib.empty() && (e = cudaMemcpy(c->ibuf.p, ib.data(), ib.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail(std::string("cudaMemcpy: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    if ((e = c->work.ensure(8)) != cudaSuccess || (e = c->counters.ensure(CN_COUNT * 8)) != cudaSuccess)
+        return bail(std::string("cudaMalloc: ") + cudaGetErrorString(e), FTSB_E_CUDA);
+    cudaMemset(c->counters.p, 0, CN_COUNT * 8);
+    const int *base = (const int *)c->ibuf.p;
+    DevProg &P = c->prog;
+    P.n_elems = c->comp.n_elems;
+    P.n_slots = c->comp.n_slots;
+    P.n_fn = c->comp.n_fn;
+    P.n_res = c->comp.n_res;
+    P.n_src = c->comp.n_src;
+    P.n_dyn = c->comp.n_dyn;
+    P.res = base + c->comp.off_res;
+    P.src = base + c->comp.off_src;
+    P.dyn = base + c->comp.off_dyn;
+    P.src_of_elem = base + c->comp.off_src_of_elem;
+    P.op = dev_mode(base, c->comp.mode[0]);
+    P.dc = dev_mode(base, c->comp.mode[1]);
+    P.tran = dev_mode(base, c->comp.mode[2]);
+    P.lay = c->comp.lay;
+    *out = c;
+    return 0;
+}
+
+void ftsb_destroy(ftsb_circuit *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream && c->own_stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
+                      &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step};
+    for (DevBuf *b : bufs) b->release();
+    delete c;
+}
+
+int32_t ftsb_n_elems(const ftsb_circuit *c) { return c ? c->comp.n_elems : -1; }
+int32_t ftsb_n_run(const ftsb_circuit *c) { return c ? c->comp.n_run : -1; }
+int32_t ftsb_n_start(const ftsb_circuit *c) { return c ? c->comp.n_start : -1; }
+int32_t ftsb_n_fn(const ftsb_circuit *c) { return c ? c->comp.n_fn : -1; }
+
+int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
+{
+    if (!c || !name) return fail(c, FTSB_E_ARG, "ftsb_set_option: null argument");
+    if (!strcmp(name, "skip_refactor"))
+        c->skip_refactor = value ? 1 : 0;
+    else if (!strcmp(name, "force_cta"))
+        c->force_cta = value ? 1 : 0;
+    else
+        return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
+    return 0;
+}
+
+int ftsb_set_params(ftsb_circuit *c, int64_t batch, const double *vals, const double *fn, int layout, int mem)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    if (batch <= 0) return fail(c, FTSB_E_ARG, "ftsb_set_params: batch must be > 0");
+    const int ne = c->comp.n_elems, nf = c->comp.n_fn;
+    if (ne > 0 && !vals) return fail(c, FTSB_E_ARG, "ftsb_set_params: vals is NULL");
+    if (nf > 0 && !fn) return fail(c, FTSB_E_ARG, "ftsb_set_params: fn is NULL but the circuit has waveform sources");
+    if (layout != FTSB_LAYOUT_INSTANCE_MAJOR && layout != FTSB_LAYOUT_PARAM_MAJOR)
+        return fail(c, FTSB_E_ARG, "ftsb_set_params: bad layout");
+    FTSB_CUDA(c, cudaSetDevice(c->device));
+    const size_t vb = (size_t)batch * std::max(ne, 1) * 8, fb = (size_t)batch * std::max(nf, 1) * 7 * 8;
+    FTSB_CUDA(c, c->vals.ensure(vb));
+    FTSB_CUDA(c, c->fn.ensure(fb));
+    const cudaMemcpyKind kind = mem == FTSB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    auto put = [&](DevBuf &dst, const double *src, long long inner) -> int {
+        if (inner == 0 || !src) return 0;
+        const size_t bytes = (size_t)batch * inner * 8;
+        if (layout == FTSB_LAYOUT_INSTANCE_MAJOR) {
+            FTSB_CUDA(c, cudaMemcpyAsync(dst.p, src, bytes, kind, c->stream));
+        } else { // [inner][batch] -> [batch][inner]
+            const double *dsrc = src;
+            if (mem == FTSB_MEM_HOST) {
+                FTSB_CUDA(c, c->tmp_in.ensure(bytes));
+                FTSB_CUDA(c, cudaMemcpyAsync(c->tmp_in.p, src, bytes, kind, c->stream));
+                dsrc = (const double *)c->tmp_in.p;
+            }
+            dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((inner + 31) / 32));
+            k_transpose<<<grid, dim3(32, 8), 0, c->stream>>>(dsrc, (double *)dst.p, inner, batch);
+            c->launches++;
+            FTSB_CUDA(c, cudaGetLastError());
+            if (mem == FTSB_MEM_HOST) FTSB_CUDA(c, cudaStreamSynchronize(c->stream)); // tmp_in is reused
+        }
+        return 0;
+    };
+    int rc = put(c->vals, vals, ne);
+    if (rc) return rc;
+    rc = put(c->fn, fn, (long long)nf * 7);
+    if (rc) return rc;
+    if (mem == FTSB_MEM_HOST) FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->batch = batch;
+    return 0;
+}
+
+int ftsb_run_op(ftsb_circuit *c, double *x, int32_t *n_iters, int32_t *status, int mem)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!x || !n_iters || !status) return fail(c, FTSB_E_ARG, "ftsb_run_op: null output");
+    const long long B = c->batch;
+    const int n = c->comp.n_start;
+    RunArgs a{};
+    a.batch = B;
+    a.vals = (const double *)c->vals.p;
+    a.fn = (const double *)c->fn.p;
+    if (mem == FTSB_MEM_HOST) {
+        FTSB_CUDA(c, c->o_x.ensure((size_t)B * std::max(n, 1) * 8));
+        FTSB_CUDA(c, c->o_it.ensure((size_t)B * 4));
+        FTSB_CUDA(c, c->o_status.ensure((size_t)B * 4));
+        a.x = (double *)c->o_x.p;
+        a.n_iters = (int *)c->o_it.p;
+        a.status = (int *)c->o_status.p;
+    } else {
+        a.x = x;
+        a.n_iters = n_iters;
+        a.status = status;
+    }
+    rc = launch(c, AN_OP, a);
+    if (rc) return rc;
+    if (mem == FTSB_MEM_HOST) {
+        FTSB_CUDA(c, cudaMemcpyAsync(x, a.x, (size_t)B * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(n_iters, a.n_iters, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(status, a.status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int ftsb_run_dc(ftsb_circuit *c, int32_t sweep_elem, const double *start, const double *stop, const double *step,
+                int64_t max_points, double *x, int32_t *n_iters, int64_t *points_done, int32_t *status, int mem)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!start || !stop || !step || !x || !n_iters || !points_done || !status)
+        return fail(c, FTSB_E_ARG, "ftsb_run_dc: null argument");
+    if (sweep_elem < 0 || sweep_elem >= c->comp.n_elems || c->comp.src_of_elem[sweep_elem] < 0)
+        return fail(c, FTSB_E_ARG, "ftsb_run_dc: sweep_elem must be a V or I source (src/spice.pest:6)");
+    if (max_points <= 0) return fail(c, FTSB_E_ARG, "ftsb_run_dc: max_points must be > 0");
+    const long long B = c->batch;
+    const int n = c->comp.n_run;
+    RunArgs a{};
+    a.batch = B;
+    a.vals = (const double *)c->vals.p;
+    a.fn = (const double *)c->fn.p;
+    a.sweep_src = c->comp.src_of_elem[sweep_elem];
+    a.max_points = max_points;
+    if (mem == FTSB_MEM_HOST) {
+        for (long long i = 0; i < B; ++i) {
+            double cnt = std::ceil((stop[i] - start[i]) / step[i]);
+            if (cnt > (double)max_points)
+                return fail(c, FTSB_E_ARG, "ftsb_run_dc: instance " + std::to_string(i) + " has more than max_points points");
+        }
+        FTSB_CUDA(c, c->i_start.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->i_stop.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->i_step.ensure((size_t)B * 8));
+        FTSB_CUDA(c, cudaMemcpyAsync(c->i_start.p, start, (size_t)B * 8, cudaMemcpyHostToDevice, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(c->i_stop.p, stop, (size_t)B * 8, cudaMemcpyHostToDevice, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(c->i_step.p, step, (size_t)B * 8, cudaMemcpyHostToDevice, c->stream));
+        FTSB_CUDA(c, c->o_x.ensure((size_t)B * max_points * std::max(n, 1) * 8));
+        FTSB_CUDA(c, c->o_it.ensure((size_t)B * max_points * 4));
+        FTSB_CUDA(c, c->o_done.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->o_status.ensure((size_t)B * 4));
+        a.start = (const double *)c->i_start.p;
+        a.stop = (const double *)c->i_stop.p;
+        a.step = (const double *)c->i_step.p;
+        a.x = (double *)c->o_x.p;
+        a.n_iters = (int *)c->o_it.p;
+        a.points_done = (long long *)c->o_done.p;
+        a.status = (int *)c->o_status.p;
+        FTSB_CUDA(c, cudaMemsetAsync(a.n_iters, 0, (size_t)B * max_points * 4, c->stream));
+        FTSB_CUDA(c, cudaMemsetAsync(a.x, 0, (size_t)B * max_points * n * 8, c->stream));
+    } else {
+        a.start = start;
+        a.stop = stop;
+        a.step = step;
+        a.x = x;
+        a.n_iters = n_iters;
+        a.points_done = (long long *)points_done;
+        a.status = status;
+    }
+    rc = launch(c, AN_DC, a);
+    if (rc) return rc;
+    if (mem == FTSB_MEM_HOST) {
+        FTSB_CUDA(c, cudaMemcpyAsync(x, a.x, (size_t)B * max_points * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(n_iters, a.n_iters, (size_t)B * max_points * 4, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(points_done, a.points_done, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(status, a.status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int ftsb_run_tran(ftsb_circuit *c, double stop, double step_max, const ftsb_tran_opts *opts, double *t, double *x,
+                  int32_t *n_iters, int64_t *n_rec, double *x_final, int32_t *status, int mem)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!n_rec || !status) return fail(c, FTSB_E_ARG, "ftsb_run_tran: n_rec and status are required");
+    const long long B = c->batch;
+    const int n = c->comp.n_run;
+    const long long cap = opts ? opts->capacity : 0;
+    if (cap < 0) return fail(c, FTSB_E_ARG, "ftsb_run_tran: negative capacity");
+    if (cap == 0) t = nullptr, x = nullptr, n_iters = nullptr;
+    RunArgs a{};
+    a.batch = B;
+    a.vals = (const double *)c->vals.p;
+    a.fn = (const double *)c->fn.p;
+    a.t_stop = stop;
+    a.step_max = step_max;
+    a.cap = cap;
+    a.rec_stride = opts ? opts->rec_stride : 1;
+    if (mem == FTSB_MEM_HOST) {
+        if (x) {
+            FTSB_CUDA(c, c->o_x.ensure((size_t)B * cap * std::max(n, 1) * 8));
+            FTSB_CUDA(c, cudaMemsetAsync(c->o_x.p, 0, (size_t)B * cap * n * 8, c->stream));
+        }
+        if (t) {
+            FTSB_CUDA(c, c->o_t.ensure((size_t)B * cap * 8));
+            FTSB_CUDA(c, cudaMemsetAsync(c->o_t.p, 0, (size_t)B * cap * 8, c->stream));
+        }
+        if (n_iters) {
+            FTSB_CUDA(c, c->o_it.ensure((size_t)B * cap * 4));
+            FTSB_CUDA(c, cudaMemsetAsync(c->o_it.p, 0, (size_t)B * cap * 4, c->stream));
+        }
+        FTSB_CUDA(c, c->o_nrec.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->o_status.ensure((size_t)B * 4));
+        if (x_final) FTSB_CUDA(c, c->o_xf.ensure((size_t)B * std::max(n, 1) * 8));
+        a.x = x ? (double *)c->o_x.p : nullptr;
+        a.t_out = t ? (double *)c->o_t.p : nullptr;
+        a.n_iters = n_iters ? (int *)c->o_it.p : nullptr;
+        a.n_rec = (long long *)c->o_nrec.p;
+        a.status = (int *)c->o_status.p;
+        a.x_final = x_final ? (double *)c->o_xf.p : nullptr;
+    } else {
+        a.x = x;
+        a.t_out = t;
+        a.n_iters = n_iters;
+        a.n_rec = (long long *)n_rec;
+        a.status = status;
+        a.x_final = x_final;
+    }
+    rc = launch(c, AN_TRAN, a);
+    if (rc) return rc;
+    if (mem == FTSB_MEM_HOST) {
+        if (x) FTSB_CUDA(c, cudaMemcpyAsync(x, a.x, (size_t)B * cap * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (t) FTSB_CUDA(c, cudaMemcpyAsync(t, a.t_out, (size_t)B * cap * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (n_iters) FTSB_CUDA(c, cudaMemcpyAsync(n_iters, a.n_iters, (size_t)B * cap * 4, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(n_rec, a.n_rec, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaMemcpyAsync(status, a.status, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (x_final) FTSB_CUDA(c, cudaMemcpyAsync(x_final, a.x_final, (size_t)B * n * 8, cudaMemcpyDeviceToHost, c->stream));
+        FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int ftsb_sync(ftsb_circuit *c)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    FTSB_CUDA(c, cudaSetDevice(c->device));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void *ftsb_stream(ftsb_circuit *c) { return c ? (void *)c->stream : nullptr; }
+
+int ftsb_set_stream(ftsb_circuit *c, void *cuda_stream)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    FTSB_CUDA(c, cudaSetDevice(c->device));
+    if (c->stream && c->own_stream) {
+        FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaStreamDestroy(c->stream);
+    }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return 0;
+}
+
+int ftsb_get_counters(ftsb_circuit *c, ftsb_counters *out)
+{
+    if (!c || !out) return fail(c, FTSB_E_ARG, "ftsb_get_counters: null argument");
+    FTSB_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long h[CN_COUNT];
+    FTSB_CUDA(c, cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    out->solve_points = (int64_t)h[CN_POINTS];
+    out->newton_iters = (int64_t)h[CN_NEWTON];
+    out->lu_factor = (int64_t)h[CN_FACTOR];
+    out->lu_solve = (int64_t)h[CN_SOLVE];
+    out->rej_newton = (int64_t)h[CN_REJ_NEWTON];
+    out->rej_plte = (int64_t)h[CN_REJ_PLTE];
+    return 0;
+}
+
+int64_t ftsb_launch_count(const ftsb_circuit *c) { return c ? c->launches : 0; }
+const char *ftsb_last_variant(const ftsb_circuit *c) { return c ? c->variant.c_str() : ""; }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// standalone batched LU solve (KATs of gauss_lu.rs:60-109) and the fp64 micro-benchmark
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+template <class Team>
+__device__ void lu_one(const Team &tm, int n, const double *a, const double *b, double *x, double *J, double *y,
+                       double *xs, int *piv)
+{
+    for (int c = 0; c < n; ++c)
+        for (int i = tm.rank; i < n; i += tm.size()) J[c * n + i] = a[i * n + c]; // row-major in, column-major J
+    for (int i = tm.rank; i < n; i += tm.size()) y[i] = b[i];
+    tm.sync();
+    int mypos = 0;
+    lu_factor(tm, n, n, J, piv, mypos);
+    lu_solve(tm, n, n, J, piv, mypos, y, xs);
+    for (int i = tm.rank; i < n; i += tm.size()) x[i] = xs[i];
+    tm.sync();
+}
+
+__global__ void __launch_bounds__(32) k_lu_warp(int n, long long batch, const double *a, const double *b, double *x)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *J = reinterpret_cast<double *>(smem_raw);
+    double *y = J + n * n;
+    double *xs = y + n;
+    int *piv = reinterpret_cast<int *>(xs + n);
+    SubWarp<32> tm;
+    for (long long s = blockIdx.x; s < batch; s += gridDim.x)
+        lu_one(tm, n, a + s * n * n, b + s * n, x + s * n, J, y, xs, piv);
+}
+
+__global__ void k_lu_cta(int n, long long batch, const double *a, const double *b, double *x, double *scratch)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *red = reinterpret_cast<double *>(smem_raw);
+    double *y = red + 96;
+    double *xs = y + n;
+    int *piv = reinterpret_cast<int *>(xs + n);
+    double *J = scratch + (size_t)blockIdx.x * n * n;
+    CtaTeam tm(red);
+    for (long long s = blockIdx.x; s < batch; s += gridDim.x)
+        lu_one(tm, n, a + s * n * n, b + s * n, x + s * n, J, y, xs, piv);
+}
+
+__global__ void k_fp64_fma(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+} // namespace
+
+extern "C" int ftsb_lu_solve(int device, int32_t n, int64_t batch, const double *a, const double *b, double *x, int mem)
+{
+    if (n <= 0 || batch <= 0 || !a || !b || !x) return fail(nullptr, FTSB_E_ARG, "ftsb_lu_solve: bad argument");
+    if (n > 1024) return fail(nullptr, FTSB_E_UNSUPPORTED, "ftsb_lu_solve: n > 1024");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(nullptr, FTSB_E_CUDA, "ftsb_lu_solve: no usable CUDA device; this library has no CPU fallback");
+    }
+#define LU_CUDA(call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(e__);                     \
+            return FTSB_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+    LU_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LU_CUDA(cudaGetDeviceProperties(&prop, device));
+    const size_t ab = (size_t)batch * n * n * 8, vb = (size_t)batch * n * 8;
+    DevBuf da, db, dx, scr;
+    const double *pa = a, *pb = b;
+    double *px = x;
+    if (mem == FTSB_MEM_HOST) {
+        LU_CUDA(da.ensure(ab));
+        LU_CUDA(db.ensure(vb));
+        LU_CUDA(dx.ensure(vb));
+        LU_CUDA(cudaMemcpy(da.p, a, ab, cudaMemcpyHostToDevice));
+        LU_CUDA(cudaMemcpy(db.p, b, vb, cudaMemcpyHostToDevice));
+        pa = (const double *)da.p;
+        pb = (const double *)db.p;
+        px = (double *)dx.p;
+    }
+    int grid = (int)std::min<long long>(batch, (long long)prop.multiProcessorCount * 8);
+    if (n <= 32) {
+        size_t smem = ((size_t)n * n + 2 * n) * 8 + (size_t)n * 4 + 16;
+        k_lu_warp<<<grid, 32, smem>>>(n, batch, pa, pb, px);
+    } else {
+        int block = ((n + 31) / 32) * 32;
+        grid = (int)std::min<long long>(batch, (long long)prop.multiProcessorCount * 2);
+        LU_CUDA(scr.ensure((size_t)grid * n * n * 8));
+        size_t smem = (96 + 2 * (size_t)n) * 8 + (size_t)n * 4 + 16;
+        k_lu_cta<<<grid, block, smem>>>(n, batch, pa, pb, px, (double *)scr.p);
+    }
+    LU_CUDA(cudaGetLastError());
+    LU_CUDA(cudaDeviceSynchronize());
+    if (mem == FTSB_MEM_HOST) LU_CUDA(cudaMemcpy(x, px, vb, cudaMemcpyDeviceToHost));
+    da.release();
+    db.release();
+    dx.release();
+    scr.release();
+    return 0;
+#undef LU_CUDA
+}
+
+extern "C" double ftsb_measure_fp64_tflops(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return -1.0;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int block = 256, grid = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double *out = nullptr;
+    if (cudaMalloc(&out, (size_t)grid * block * 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_fma<<<grid, block>>>(out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 8.0 * (double)iters * (double)grid * block;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}

@@ -1,0 +1,311 @@
+"""GPU parity tests (run on the B200 with ``pytest -m gpu``): the CUDA path, called through the C-ABI
+(libftsb.so via ctypes), against the CPU oracle on the same inputs and against the committed golden
+fixtures.  Bar (north_star / SURVEY.md §8d): every unknown within 1e-9 relative + 1e-12 absolute, EQUAL
+Newton iteration counts per solve point, equal record / point counts, equal per-instance status, and for
+.tran equal time stamps."""
+import numpy as np
+import pytest
+
+from ftspice_b200 import capi
+from ftspice_b200 import netlist as nl
+from ftspice_b200.engine import BatchEngine, Engine, NotConvergedError, lu_solve
+
+from harness import ATOL, RTOL, assert_close, fl, golden, load, netlist_names
+
+pytestmark = pytest.mark.gpu
+
+NAMES = netlist_names()
+OP_NAMES = [n for n in NAMES if "op" in golden()[n]]
+DC_NAMES = [n for n in NAMES if "dc" in golden()[n]]
+TRAN_NAMES = [n for n in NAMES if "tran" in golden()[n]]
+
+
+def test_library_has_device():
+    assert capi.lib().ftsb_device_count() >= 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# the reference's own LU known-answer tests (src/engine/gauss_lu.rs:60-109) on the GPU kernel
+# ------------------------------------------------------------------------------------------------------
+def test_lu_kats():
+    x = lu_solve(np.eye(2), np.zeros(2))
+    assert (x[0] == 0).all()
+    x = lu_solve(np.eye(2), np.array([1.0, 2.0]))
+    assert (x[0] == [1.0, 2.0]).all()
+    x = lu_solve(np.array([[5.0, 2.0], [-1.0, 3.0]]), np.array([1.0, 2.0]))
+    assert abs(x[0, 0] - (-1.0 / 17.0)) < 1e-15 and abs(x[0, 1] - 11.0 / 17.0) < 1e-15
+    x = lu_solve(np.array([[5.0, 2.0, 1.0], [-1.0, 3.0, -1.0], [0.0, 2.0, -1.0]]), np.array([1.0, 2.0, 1.0]))
+    assert np.abs(x[0] - np.array([-2.0 / 9.0, 7.0 / 9.0, 5.0 / 9.0])).max() < 1e-15
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 14, 17, 32, 33, 65, 100])
+def test_lu_random_vs_oracle(n, oracle_mod):
+    import ctypes as ct
+    rng = np.random.default_rng(1234 + n)
+    B = 64
+    a = rng.standard_normal((B, n, n))
+    a[:, np.arange(n), np.arange(n)] += 0.5
+    if n >= 3:  # exact ties in the pivot column: first-max-wins rule
+        a[0, :, 0] = 1.0
+        a[1, 1, 0] = a[1, 2, 0] = -3.0
+    b = rng.standard_normal((B, n))
+    x = lu_solve(a, b)
+    L = oracle_mod.lib()
+    dp = ct.POINTER(ct.c_double)
+    for i in range(B):
+        ai, bi, xi = a[i].copy(), b[i].copy(), np.zeros(n)
+        L.orc_lu_solve(n, ai.ctypes.data_as(dp), bi.ctypes.data_as(dp), xi.ctypes.data_as(dp))
+        # same pivots, same operation order, no FMA contraction on either side -> the same bits
+        assert np.array_equal(x[i], xi), (n, i, np.abs(x[i] - xi).max())
+
+
+# ------------------------------------------------------------------------------------------------------
+# the 17 reference netlists, single instance, vs golden fixtures and vs the live oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", OP_NAMES)
+def test_op_reference_netlists(name, oracle_mod):
+    g = golden()[name]["op"]
+    circ = load(name)
+    be = BatchEngine(circ)
+    be.set_params()
+    r = be.run_op()
+    assert int(r.status[0]) == g["status"], (name, capi.STATUS[int(r.status[0])])
+    s, it, x, _ = oracle_mod.Oracle(circ).run_op()
+    assert s == g["status"]
+    if g["status"] == 0:
+        assert int(r.n_iters[0]) == g["n_iters"] == it
+        assert_close(r.x[0], fl(g["x"]), f"{name} .op vs golden")
+        assert_close(r.x[0], x, f"{name} .op vs oracle")
+
+
+@pytest.mark.parametrize("name", DC_NAMES)
+def test_dc_reference_netlists(name):
+    g = golden()[name]["dc"]
+    circ = load(name)
+    d = circ.command("dc")
+    be = BatchEngine(circ)
+    be.set_params()
+    r = be.run_dc(d.source, d.start, d.stop, d.step)
+    assert int(r.status[0]) == g["status"]
+    k = int(r.points_done[0])
+    assert k == len(g["n_iters"])
+    if k:
+        assert (r.n_iters[0, :k] == np.array(g["n_iters"])).all()
+        assert_close(r.x[0, :k], fl(g["x"]), f"{name} .dc vs golden")
+        assert (r.sweep[0, :k] == fl(g["sweep"])).all()
+
+
+@pytest.mark.parametrize("name", TRAN_NAMES)
+def test_tran_reference_netlists(name):
+    g = golden()[name]["tran"]
+    circ = load(name)
+    tr = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params()
+    r = be.run_tran(tr.stop, tr.step, capacity=max(g["n_rec"], 1) + 8)
+    assert int(r.status[0]) == g["status"]
+    k = int(r.n_rec[0])
+    assert k == g["n_rec"]
+    if k:
+        assert (r.n_iters[0, :k] == np.array(g["n_iters"])).all()
+        assert (r.t[0, :k] == fl(g["t"])).all(), "time stamps must be bit-equal"
+        assert_close(r.x[0, :k], fl(g["x"]), f"{name} .tran vs golden")
+        assert_close(r.x_final[0], fl(g["x"])[-1], f"{name} final")
+    c = be.counters()
+    assert c["solve_points"] == k
+    assert c["rej_newton"] == g["rej_newton"] and c["rej_plte"] == g["rej_plte"]
+
+
+def test_refactor_skip_is_bit_identical():
+    """Skipping bit-identical refactorisations (linear circuits) must not change a single bit."""
+    for name in ("rc_pulse", "rl", "v_divider_sweep"):
+        circ = load(name)
+        res = []
+        for skip in (1, 0):
+            be = BatchEngine(circ)
+            be.set_option("skip_refactor", skip)
+            be.set_params()
+            if circ.command("tran"):
+                tr = circ.command("tran")
+                r = be.run_tran(tr.stop, tr.step, capacity=1024)
+                res.append((r.n_rec.copy(), r.t.copy(), r.x.copy(), r.n_iters.copy(), be.counters()))
+            else:
+                d = circ.command("dc")
+                r = be.run_dc(d.source, d.start, d.stop, d.step)
+                res.append((r.points_done.copy(), r.sweep.copy(), r.x.copy(), r.n_iters.copy(), be.counters()))
+        for a, b in zip(res[0][:4], res[1][:4]):
+            assert np.array_equal(a, b)
+        assert res[0][4]["lu_factor"] < res[1][4]["lu_factor"]
+        assert res[1][4]["lu_factor"] == res[1][4]["newton_iters"]
+
+
+# ------------------------------------------------------------------------------------------------------
+# Engine mirror: reference-format CSV and error behaviour
+# ------------------------------------------------------------------------------------------------------
+def test_engine_mirror_csv_and_errors():
+    g = golden()
+    e = Engine.from_netlist(g["v_divider_sweep"]["netlist"])
+    csv = e.run_op().to_csv().splitlines()
+    assert csv[0] == "n_iters,1,2,V1"
+    assert csv[1].startswith("30,3.99999999")
+    dc = e.run_dc()
+    assert len(dc.data) == 100 and dc.headers == ["n_iters", "1", "2", "V1"]
+    assert dc.to_csv().splitlines()[1] == "1,0,0,0"
+    with pytest.raises(NotConvergedError):  # no current-type unknown -> NaN norm (Q3)
+        Engine.from_netlist(g["i_divider"]["netlist"]).run_op()
+    tr = Engine.from_netlist(g["rc"]["netlist"]).run_tran()
+    assert tr.headers[:2] == ["n_iters", "t"] and len(tr.data) == g["rc"]["tran"]["n_rec"]
+    assert tr.to_csv().splitlines()[1].split(",")[1] == "0.000000000000000001"
+
+
+# ------------------------------------------------------------------------------------------------------
+# batches: Monte-Carlo .op (config C2), sweep chains (C3), parallel .tran (C4 shape, small)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["proj1", "proj1_nl", "npn_test", "nmos_test", "proj2", "r_d_direct"])
+def test_monte_carlo_op_batch(which, oracle_mod):
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else load(which)
+    B = 512
+    vals, fns = nl.monte_carlo(circ, B)
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    r = be.run_op()
+    st, it, x = oracle_mod.Oracle(circ).batch_op(vals, fns, threads=8)
+    assert (r.status == st).all()
+    ok = st == 0
+    assert ok.sum() > 0.9 * B
+    assert (r.n_iters[ok] == it[ok]).all()
+    assert_close(r.x[ok], x[ok], f"{which} Monte-Carlo .op")
+    assert be.counters()["solve_points"] == int(ok.sum())
+
+
+def test_dc_chains_nmos(oracle_mod):
+    """C3 shape: nmos_test.sp swept on V01, cut into chains (cold start at each chain head)."""
+    circ = load("nmos_test")
+    C, Lp = 64, 16
+    width = 3.4 / C
+    start = np.arange(C) * width
+    step = np.full(C, width / Lp)
+    stop = start + width - 0.25 * step  # ceil((stop-start)/step) == Lp
+    vals = np.broadcast_to(circ.vals, (C, circ.n_elems)).copy()
+    be = BatchEngine(circ)
+    be.set_params(vals)
+    se = circ.elem_index("V01")
+    r = be.run_dc(se, start, stop, step)
+    st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, None, se, start, stop, step, Lp, threads=8)
+    assert (r.status == st).all() and (r.points_done == done).all()
+    assert (done == Lp).all()
+    assert (r.n_iters == it).all()
+    assert_close(r.x, x, "nmos .dc chains")
+
+
+def test_dc_failure_stops_chain(oracle_mod):
+    """Q18: the chain that crosses 3.48 V dies there; status and points_done must match the reference."""
+    circ = load("nmos_test")
+    start = np.array([3.40, 0.0])
+    stop = np.array([3.60, 0.2])
+    step = np.array([0.01, 0.01])
+    vals = np.broadcast_to(circ.vals, (2, circ.n_elems)).copy()
+    se = circ.elem_index("V01")
+    be = BatchEngine(circ)
+    be.set_params(vals)
+    r = be.run_dc(se, start, stop, step, max_points=32)
+    st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, None, se, start, stop, step, 32, threads=1)
+    assert (r.status == st).all() and (r.points_done == done).all()
+    assert st[0] == capi.NOT_CONVERGED and st[1] == capi.OK
+    for i in range(2):
+        k = int(done[i])
+        assert (r.n_iters[i, :k] == it[i, :k]).all()
+        assert_close(r.x[i, :k], x[i, :k], "partial chain")
+
+
+@pytest.mark.parametrize("drive", ["SIN( 0.0 1.0 10M )", "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )"])
+@pytest.mark.parametrize("nodes", [8, 24, 64])
+def test_tran_ladder_batch(nodes, drive, oracle_mod):
+    """C4 shape at reduced length: RC/RL ladder, Monte-Carlo values, full waveform parity."""
+    circ = nl.load(nl.ladder_netlist(nodes, drive, stop="60n", step="1n"))
+    B = 6
+    vals, fns = nl.monte_carlo(circ, B)
+    tr = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    cap = 400
+    r = be.run_tran(tr.stop, tr.step, capacity=cap)
+    st, nrec, it, t, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals, fns, tr.stop, tr.step, cap, threads=6)
+    assert (r.status == st).all()
+    assert (r.n_rec == nrec).all(), (r.n_rec, nrec)
+    assert (nrec < cap).all()
+    for i in range(B):
+        k = int(nrec[i])
+        assert (r.n_iters[i, :k] == it[i, :k]).all()
+        assert (r.t[i, :k] == t[i, :k]).all()
+        assert_close(r.x[i, :k], x[i, :k], f"ladder{nodes} instance {i}")
+    assert_close(r.x_final, xf, "x_final")
+
+
+def test_tran_record_stride(oracle_mod):
+    circ = load("rc_sine")
+    tr = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(batch=3)
+    full = be.run_tran(tr.stop, tr.step, capacity=512)
+    dec = be.run_tran(tr.stop, tr.step, capacity=512, rec_stride=4)
+    none = be.run_tran(tr.stop, tr.step, want_wave=False)
+    assert (dec.n_rec == full.n_rec).all() and (none.n_rec == full.n_rec).all()
+    k = int(full.n_rec[0])
+    kd = (k + 3) // 4
+    assert np.array_equal(dec.t[:, :kd], full.t[:, 0:k:4])
+    assert np.array_equal(dec.x[:, :kd], full.x[:, 0:k:4])
+    assert np.array_equal(none.x_final, full.x_final)
+
+
+def test_tran_inverter_chain_small(oracle_mod):
+    """C5 shape at reduced size: NMOS inverter chain (CTA path), nonlinear + dynamic."""
+    circ = nl.load(nl.inverter_chain_netlist(40, stop="3n", step="50p"))
+    B = 3
+    vals, fns = nl.monte_carlo(circ, B)
+    tr = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    cap = 256
+    r = be.run_tran(tr.stop, tr.step, capacity=cap)
+    st, nrec, it, t, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals, fns, tr.stop, tr.step, cap, threads=3)
+    assert (r.status == st).all() and (r.n_rec == nrec).all()
+    for i in range(B):
+        k = int(nrec[i])
+        assert (r.n_iters[i, :k] == it[i, :k]).all()
+        assert (r.t[i, :k] == t[i, :k]).all()
+        assert_close(r.x[i, :k], x[i, :k], f"inverter chain instance {i}")
+
+
+def test_param_major_layout_and_device_buffers():
+    """ftsb_set_params(PARAM_MAJOR) and FTSB_MEM_DEVICE buffers give the same bits as the host path."""
+    import torch
+    circ = nl.load(nl.PROJ1_NL)
+    B = 300
+    vals, fns = nl.monte_carlo(circ, B)
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    ref = be.run_op()
+    dv = torch.from_numpy(np.ascontiguousarray(vals.T)).cuda()  # [elem][instance]
+    be2 = BatchEngine(circ)
+    be2.set_params_device(B, dv.data_ptr(), 0, capi.LAYOUT_PARAM_MAJOR)
+    x = torch.empty((B, circ.n_start), dtype=torch.float64, device="cuda")
+    it = torch.empty(B, dtype=torch.int32, device="cuda")
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    be2.run_op_device(x.data_ptr(), it.data_ptr(), st.data_ptr())
+    be2.sync()
+    assert np.array_equal(x.cpu().numpy(), ref.x)
+    assert np.array_equal(it.cpu().numpy(), ref.n_iters)
+    assert np.array_equal(st.cpu().numpy(), ref.status)
+
+
+def test_api_errors():
+    circ = load("v_divider")
+    be = BatchEngine(circ)
+    with pytest.raises(capi.FtsbError) as ei:
+        be.run_op()  # before set_params
+    assert ei.value.code == capi.E_STATE
+    be.set_params()
+    with pytest.raises(capi.FtsbError) as ei:
+        be.run_dc(circ.elem_index("R12"), 0.0, 1.0, 0.1)  # not a source
+    assert ei.value.code == capi.E_ARG
