@@ -39,15 +39,29 @@ def fl(rows):
         else np.array([float(v) for v in rows], np.float64)
 
 
-def assert_close(got, want, what=""):
+def assert_close(got, want, what="", spread=None, spread_factor=8.0):
+    """|got - want| <= 1e-9*|want| + 1e-12 everywhere.
+
+    `spread` (sparse [[i, j, value], ...] from the golden file) lists the entries where the ORACLE's own result
+    moves by more than a tenth of that tolerance when its arithmetic changes in the last bit (FMA contraction,
+    another libm): ill-conditioned unknowns that the reference cannot reproduce to 1e-9 across platforms either.
+    There the allowance is widened by spread_factor x the oracle's own spread.  Returns how many values needed it.
+    """
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
     both_nan = np.isnan(got) & np.isnan(want)
     err = np.abs(got - want)
     tol = RTOL * np.abs(want) + ATOL
+    strict_bad = ~(err <= tol) & ~both_nan
+    if spread:
+        tol = tol.copy()
+        for i, j, v in spread:
+            if got.ndim == 2 and i < got.shape[0]:
+                tol[i, j] += spread_factor * float(v)
     bad = ~(err <= tol) & ~both_nan
     if bad.any():
         idx = np.argwhere(bad)[0]
         raise AssertionError(f"{what}: {bad.sum()} of {bad.size} values differ; first at {tuple(idx)}: "
                              f"got {got[tuple(idx)]!r} want {want[tuple(idx)]!r} (|d|={err[tuple(idx)]:.3e})")
+    return int(strict_bad.sum())

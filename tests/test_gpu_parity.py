@@ -91,7 +91,10 @@ def test_dc_reference_netlists(name):
     assert k == len(g["n_iters"])
     if k:
         assert (r.n_iters[0, :k] == np.array(g["n_iters"])).all()
-        assert_close(r.x[0, :k], fl(g["x"]), f"{name} .dc vs golden")
+        relaxed = assert_close(r.x[0, :k], fl(g["x"]), f"{name} .dc vs golden", spread=g.get("spread"))
+        # only the oracle-flagged ill-conditioned entries may use the widened allowance (proj2: node 7 floats
+        # while M720 sits at its cut-off edge; the reference's own FMA build moves it by 3e-6 there)
+        assert relaxed <= len(g.get("spread", [])), relaxed
         assert (r.sweep[0, :k] == fl(g["sweep"])).all()
 
 
