@@ -761,6 +761,75 @@ static void get_err(const mna_t *mna, const elem_t *elems, const double *x, doub
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * element-level hooks for the reference's device unit tests (src/device/<kind>.rs `mod tests`)
+ * op: 0 linear_stamp, 1 undo_linear_stamp, 2 linear_startup_stamp, 3 dynamic_stamp,
+ *     4 undo_dynamic_stamp, 5 nonlinear_stamp.  u, i = the Cap/Ind state (u_curr, i_curr).
+ * ---------------------------------------------------------------------------------------- */
+static void elem_from(elem_t *e, const orc_elem_t *oe, double u, double i)
+{
+    memset(e, 0, sizeof *e);
+    e->kind = oe->kind;
+    memcpy(e->node, oe->node, sizeof e->node);
+    e->branch = oe->branch;
+    e->fn_kind = oe->fn_kind;
+    e->val = oe->val;
+    memcpy(e->fn, oe->fn, sizeof e->fn);
+    e->u_curr = u;
+    e->i_curr = i;
+}
+
+int orc_elem_apply(const orc_elem_t *oe, double u, double i, int op, int n, const double *x, double h, double *a,
+                   double *b)
+{
+    elem_t e;
+    elem_from(&e, oe, u, i);
+    tl_panic = 0;
+    switch (op) {
+    case 0: linear_stamp(&e, n, a, b); break;
+    case 1: undo_linear_stamp(&e, n, a, b); break;
+    case 2: linear_startup_stamp(&e, n, a, b); break;
+    case 3: dynamic_stamp(&e, h, n, a, b, 0); break;
+    case 4: dynamic_stamp(&e, h, n, a, b, 1); break;
+    case 5: nonlinear_stamp(&e, x, n, a, b); break;
+    default: return -1;
+    }
+    return tl_panic;
+}
+
+/* nonlinear_funcs into hmat[n*m] starting at column col0; evaluates the closures at x into gvals.
+ * Returns count_nonlinear_funcs(). */
+int orc_elem_funcs(const orc_elem_t *oe, int n, int m, int col0, const double *x, double *hmat, double *gvals)
+{
+    elem_t e;
+    elem_from(&e, oe, 0.0, 0.0);
+    mna_t mna;
+    mna.n = n;
+    mna.m = m;
+    mna.a = NULL;
+    mna.b = NULL;
+    mna.h = hmat;
+    gfn_t g[64];
+    if (col0 < 0 || col0 > 60) return -1;
+    mna.g = g;
+    mna.g_len = col0; /* g_vec.len() at the time of the call */
+    nonlinear_funcs(&e, 0, &mna);
+    int cnt = mna.g_len - col0;
+    tl_panic = 0;
+    if (x && gvals)
+        for (int k = 0; k < cnt; k++) gvals[k] = eval_g(&e, (gfn_t){0, k}, x);
+    return cnt;
+}
+
+/* mna.rs:25-29 with caller-supplied g values: out = a.dot(x) + h.dot(g) - b  (KAT mna.rs:36-52) */
+void orc_get_err_raw(int n, int m, const double *a, const double *b, const double *h, const double *gval,
+                     const double *x, double *out)
+{
+    for (int i = 0; i < n; i++)
+        out[i] = orc_unrolled_dot(&a[(size_t)i * n], x, n) + orc_unrolled_dot(&h[(size_t)i * m], gval, m) - b[i];
+}
+
 /* ------------------------------------------------------------------------------------------
  * node collection (index-lowered): class + BTreeMap value order
  * ---------------------------------------------------------------------------------------- */

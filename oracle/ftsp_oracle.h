@@ -86,6 +86,14 @@ void orc_npn_model(double vc, double vb, double ve, double out[9]);
 /* out: ie, ic, ib, gee, gec, gce, gcc, ie_eq, ic_eq */
 int orc_nmos_model(double vd, double vg, double vs, double out[4]); /* id, gds, gm, ieq; ret !=0 → unreachable */
 
+/* element-level hooks for the reference's device unit tests; op: 0 linear_stamp, 1 undo_linear_stamp,
+ * 2 linear_startup_stamp, 3 dynamic_stamp, 4 undo_dynamic_stamp, 5 nonlinear_stamp */
+int orc_elem_apply(const orc_elem_t *e, double u_curr, double i_curr, int op, int n, const double *x, double h,
+                   double *a, double *b);
+int orc_elem_funcs(const orc_elem_t *e, int n, int m, int col0, const double *x, double *hmat, double *gvals);
+void orc_get_err_raw(int n, int m, const double *a, const double *b, const double *h, const double *gval,
+                     const double *x, double *out);
+
 /* ---- the three analyses (src/engine.rs:62-206) ---- */
 /* x_out[n_start]; n_iters_out single */
 int orc_run_op(const orc_circuit_t *c, double *x_out, int64_t *n_iters_out, orc_stats_t *st);

@@ -73,6 +73,12 @@ def lib() -> ct.CDLL:
         _lib.orc_npn_model.restype = None
         _lib.orc_nmos_model.argtypes = [d, d, d, P(d)]
         _lib.orc_nmos_model.restype = ct.c_int
+        _lib.orc_elem_apply.argtypes = [P(OrcElem), d, d, ct.c_int, ct.c_int, P(d), d, P(d), P(d)]
+        _lib.orc_elem_apply.restype = ct.c_int
+        _lib.orc_elem_funcs.argtypes = [P(OrcElem), ct.c_int, ct.c_int, ct.c_int, P(d), P(d), P(d)]
+        _lib.orc_elem_funcs.restype = ct.c_int
+        _lib.orc_get_err_raw.argtypes = [ct.c_int, ct.c_int, P(d), P(d), P(d), P(d), P(d), P(d)]
+        _lib.orc_get_err_raw.restype = None
         _lib.orc_dc_count.argtypes = [d, d, d]
         _lib.orc_dc_count.restype = i64
         _lib.orc_run_op.argtypes = [P(OrcCircuit), P(d), P(i64), P(OrcStats)]
