@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. lanes=2, force_generic=1)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -259,6 +260,9 @@ def main():
     B = wl["batch"]
     first = rank * B
     be = BatchEngine(circ, device=local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        be.set_option(k, int(v))
     stream = torch.cuda.Stream(device=dev)
     capi.check(capi.lib().ftsb_set_stream(be.h, stream.cuda_stream), be.h)
     n_out = circ.n_start if wl["kind"] == "op" else circ.n_run

@@ -11,7 +11,7 @@
 
 #include "../../include/ftsb.h"
 #include "compile.h"
-#include "engine.cuh"
+#include "solver_lanes.cuh"
 
 using namespace ftsb;
 
@@ -56,11 +56,14 @@ struct ftsb_circuit {
     DevBuf vals, fn, tmp_in, work, counters, scratch;
     // staging of outputs when the caller's buffers are on the host
     DevBuf o_x, o_it, o_status, o_done, o_t, o_nrec, o_xf, i_start, i_stop, i_step;
+    DevBuf s_x, s_it, s_st; // start-up solutions of .tran (small-circuit kernels)
     std::string err;
     std::string variant = "none";
     long long launches = 0;
     int skip_refactor = 1;
     int force_cta = 0;
+    int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
+    int lanes = 0;         // >0: lanes per instance requested for the small-circuit kernels (if built)
 };
 
 #define FTSB_CUDA(c, call)                                                                        \
@@ -111,11 +114,12 @@ ModeProg dev_mode(const int *base, const ModeOff &o)
     m.b_all = dev_gather(base, o.b_all);
     m.r_nl = dev_gather(base, o.r_nl);
     m.f_nl = dev_gather(base, o.f_nl);
+    m.J_full = dev_gather(base, o.J_full);
+    m.Ax = dev_gather(base, o.Ax);
     return m;
 }
 
 // ---- kernel variants -------------------------------------------------------------------------------------
-typedef void (*KernelFn)(const RunArgs);
 
 template <int AN>
 KernelFn subwarp_kernel(int g)
@@ -139,13 +143,67 @@ KernelFn pick_kernel(int an, int g /*0 = cta*/)
 }
 
 struct LaunchPlan {
+    KernelFn fn = nullptr;
     int g = 0; // sub-warp group size, 0 = CTA team
     int block = 128;
     int grid = 1;
     size_t smem = 0;
     Layout lay;
     size_t scratch_bytes = 0;
+    bool lanes = false; // small-circuit kernel: .tran needs the start-up .op as a separate launch
 };
+
+// small-circuit kernels (solver_lanes.cuh): n <= 16, G lanes per instance.  Returns 0 when chosen.
+KernelFn find_lanes_kernel(int g, int nc, int an)
+{
+    KernelFn fn = lanes_kernel_a(g, nc, an);
+    if (!fn) fn = lanes_kernel_b(g, nc, an);
+    if (!fn) fn = lanes_kernel_c(g, nc, an);
+    if (!fn) fn = lanes_kernel_d(g, nc, an);
+    if (!fn) fn = lanes_kernel_e(g, nc, an);
+    return fn;
+}
+
+int plan_lanes(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
+{
+    const int n_start = std::max(c->comp.n_start, 1);
+    const int n = an == AN_OP ? n_start : c->comp.n_run; // exact unknown count of the analysis mode
+    if (n_start > 16 || n < 1) return 1;
+    int g = c->lanes > 0 ? c->lanes : (n <= 4 ? 1 : n <= 8 ? 2 : 4);
+    KernelFn fn = find_lanes_kernel(g, n, an);
+    if (!fn && c->lanes > 0) { // requested lane count not built: fall back to the default
+        g = n <= 4 ? 1 : n <= 8 ? 2 : 4;
+        fn = find_lanes_kernel(g, n, an);
+    }
+    if (!fn) return 1;
+    const LaneLayout T = lane_layout(n, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    const size_t smem = (size_t)T.doubles * (32 / g) * 8;
+    if (smem > c->smem_optin) return 1;
+    if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    pl.fn = fn;
+    pl.g = g;
+    pl.block = 32;
+    pl.smem = smem;
+    pl.lay = c->comp.lay;
+    pl.lay.mat_in_smem = 1;
+    pl.lay.bytes = (int)smem;
+    pl.scratch_bytes = 0;
+    pl.lanes = true;
+    const int per_warp = 32 / g;
+    long long need = (batch + per_warp - 1) / per_warp;
+    pl.grid = (int)std::max(1LL, std::min(need, (long long)occ * c->sm_count));
+    c->variant = std::string(an == AN_TRAN ? "lanes" : "sync") + std::to_string(g) + "n" + std::to_string(n) + "/occ" +
+                 std::to_string(occ);
+    return 0;
+}
 
 int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
 {
@@ -156,6 +214,7 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     const size_t int_bytes = (size_t)L.ints * 4;
     int g = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 0;
     if (c->force_cta) g = 0;
+    if (g && !c->force_generic && plan_lanes(c, an, batch, pl) == 0) return 0;
     if (g) {
         size_t per = (vec_bytes + mat_bytes + int_bytes + 15) & ~(size_t)15;
         int teams = 128 / g;
@@ -169,6 +228,7 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
             pl.lay = L;
             pl.scratch_bytes = 0;
             KernelFn fn = pick_kernel(an, g);
+            pl.fn = fn;
             cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
             if (e != cudaSuccess) return fail(c, FTSB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
             int occ = 0;
@@ -193,6 +253,7 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     L.bytes = (int)pl.smem;
     pl.lay = L;
     KernelFn fn = pick_kernel(an, 0);
+    pl.fn = fn;
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return fail(c, FTSB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     int occ = 0;
@@ -203,6 +264,8 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     c->variant = std::string("cta") + std::to_string(block) + (L.mat_in_smem ? "" : "g");
     return 0;
 }
+
+static std::string po_variant_tag(const LaunchPlan &po) { return "op" + std::to_string(po.g); }
 
 int launch(ftsb_circuit *c, int an, RunArgs &a)
 {
@@ -218,7 +281,32 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
     a.skip_refactor = c->skip_refactor;
     FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
     FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
-    KernelFn fn = pick_kernel(an, pl.g);
+    if (pl.lanes && an == AN_TRAN) {
+        // start-up solutions (engine.rs:158-161) by the .op kernel, kept on the device for the .tran kernel
+        const std::string tran_variant = c->variant;
+        LaunchPlan po;
+        if (plan_lanes(c, AN_OP, a.batch, po) != 0) return fail(c, FTSB_E_UNSUPPORTED, "no start-up kernel for this circuit");
+        const int ns = std::max(c->comp.n_start, 1);
+        FTSB_CUDA(c, c->s_x.ensure((size_t)a.batch * ns * 8));
+        FTSB_CUDA(c, c->s_it.ensure((size_t)a.batch * 4));
+        FTSB_CUDA(c, c->s_st.ensure((size_t)a.batch * 4));
+        RunArgs ao = a;
+        ao.prog.lay = po.lay;
+        ao.x = (double *)c->s_x.p;
+        ao.n_iters = (int *)c->s_it.p;
+        ao.status = (int *)c->s_st.p;
+        void *oargs[] = {&ao};
+        FTSB_CUDA(c, cudaLaunchKernel((const void *)po.fn, dim3(po.grid), dim3(po.block), oargs, po.smem, c->stream));
+        c->launches++;
+        FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+        // the start-up solve is not an output row of .tran
+        FTSB_CUDA(c, cudaMemsetAsync((unsigned long long *)c->counters.p + CN_POINTS, 0, 8, c->stream));
+        a.x_start = (const double *)c->s_x.p;
+        a.start_status = (const int *)c->s_st.p;
+        a.n_start = ns;
+        c->variant = tran_variant + "+" + po_variant_tag(po);
+    }
+    KernelFn fn = pl.fn;
     void *args[] = {&a};
     FTSB_CUDA(c, cudaLaunchKernel((const void *)fn, dim3(pl.grid), dim3(pl.block), args, pl.smem, c->stream));
     c->launches++;
@@ -288,7 +376,8 @@ int ftsb_compile(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t
     ftsb_circuit *c = new ftsb_circuit();
     c->device = device;
     std::string err;
-    if (!compile_circuit(reinterpret_cast<const ElemDesc *>(elems), n_elems, n_run, n_start, row_class, c->comp, err)) {
+    const int ld_min = 0;
+    if (!compile_circuit(reinterpret_cast<const ElemDesc *>(elems), n_elems, n_run, n_start, row_class, ld_min, c->comp, err)) {
         delete c;
         return fail(nullptr, FTSB_E_ARG, err);
     }
@@ -343,7 +432,8 @@ void ftsb_destroy(ftsb_circuit *c)
         cudaStreamDestroy(c->stream);
     }
     DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
-                      &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step};
+                      &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
+                      &c->s_st};
     for (DevBuf *b : bufs) b->release();
     delete c;
 }
@@ -360,6 +450,10 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->skip_refactor = value ? 1 : 0;
     else if (!strcmp(name, "force_cta"))
         c->force_cta = value ? 1 : 0;
+    else if (!strcmp(name, "force_generic"))
+        c->force_generic = value ? 1 : 0;
+    else if (!strcmp(name, "lanes"))
+        c->lanes = (int)value;
     else
         return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
     return 0;

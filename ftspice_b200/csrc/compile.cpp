@@ -35,7 +35,7 @@ struct ModeBuild {
     void A(int row, int col, int slot, bool neg, int phase)
     {
         if (row < 0 || col < 0) return;
-        a.push_back({col * ld + row, (unsigned)slot | (neg ? CON_NEG : 0u), phase});
+        a.push_back({row | (col << 16), (unsigned)slot | (neg ? CON_NEG : 0u), phase}); // ld-independent
     }
     void B(int row, int slot, bool neg, int phase)
     {
@@ -98,8 +98,8 @@ static void put_gather(Compiled::Impl &im, const GatherBuild &g, GatherOff &o)
     o.con = im.push(g.con);
 }
 
-bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start, const int *row_class, Compiled &out,
-                     std::string &err)
+bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start, const int *row_class, int ld_min,
+                     Compiled &out, std::string &err)
 {
     if (n_elems < 0 || n_run < 0 || n_start < n_run) {
         err = "ftsb_compile: need 0 <= n_run <= n_start";
@@ -116,7 +116,7 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
     out.n_run = n_run;
     out.n_start = n_start;
 
-    const int ld = std::max(n_start, 1);
+    const int ld = std::max(std::max(n_start, 1), ld_min); // register kernels pad the rows to lanes x rows-per-lane
     ModeBuild mb[3]; // 0 op, 1 dc, 2 tran
     mb[0].n = n_start;
     mb[1].n = n_run;
@@ -332,28 +332,68 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
         put_gather(im, make_gather(m.a, DYN, (1u << LIN) | (1u << DYN)), o.A_dyn);
         put_gather(im, make_gather(m.a, NL, 1u << NL), o.J_nl);
         {
-            // b_all: every row that has any linear or companion contribution
-            std::vector<Con> bl;
-            for (const Con &c : m.b)
-                if (c.phase != NL) bl.push_back({c.dst, c.word, c.phase == DYN ? DYN : LIN});
-            // mark all as wanted: build with need_phase satisfied for both phases
-            std::vector<Con> tagged = bl;
+            // b_all, row-indexed: b[row] = linear then companion rhs terms (rows without sources are empty)
             GatherBuild g;
-            {
-                std::map<int, std::vector<const Con *>> by_dst;
-                for (const Con &c : tagged) by_dst[c.dst].push_back(&c);
-                g.ptr.push_back(0);
-                for (auto &kv : by_dst) {
-                    g.dst.push_back(kv.first);
-                    for (int ph = 0; ph < 2; ++ph)
-                        for (const Con *c : kv.second)
-                            if (c->phase == ph) g.con.push_back((int)c->word);
-                    g.ptr.push_back((int)g.con.size());
-                }
+            g.ptr.push_back(0);
+            for (int row = 0; row < m.n; ++row) {
+                g.dst.push_back(row);
+                for (int ph = 0; ph < 2; ++ph)
+                    for (const Con &c : m.b)
+                        if (c.phase == ph && c.dst == row) g.con.push_back((int)c.word);
+                g.ptr.push_back((int)g.con.size());
             }
             put_gather(im, g, o.b_all);
         }
-        put_gather(im, make_gather(m.b, NL, 1u << NL), o.r_nl);
+        {
+            // J_full: every structurally non-zero entry, all phases in order (linear, companion, nonlinear)
+            std::vector<Con> all = m.a;
+            for (Con &c : all) c.phase = 0;
+            GatherBuild g;
+            std::map<int, std::vector<const Con *>> by_dst;
+            for (const Con &c : m.a) by_dst[c.dst].push_back(&c);
+            g.ptr.push_back(0);
+            for (auto &kv : by_dst) {
+                g.dst.push_back(kv.first);
+                for (int ph = 0; ph < 3; ++ph)
+                    for (const Con *c : kv.second)
+                        if (c->phase == ph) g.con.push_back((int)c->word);
+                g.ptr.push_back((int)g.con.size());
+            }
+            put_gather(im, g, o.J_full);
+        }
+        {
+            // Ax, row-indexed flat list of (col, slot, sign) for the linear + companion part
+            GatherBuild g;
+            g.ptr.push_back(0);
+            for (int row = 0; row < m.n; ++row) {
+                g.dst.push_back(row);
+                for (int ph = 0; ph < 2; ++ph)
+                    for (const Con &c : m.a) {
+                        const int r = c.dst & 0xffff, col = c.dst >> 16;
+                        if (c.phase == ph && r == row) {
+                            if ((c.word & ~CON_NEG) > AX_SLOT_MASK || col >= (1 << (31 - AX_COL_SHIFT))) {
+                                err = "ftsb_compile: circuit too large for the packed A*x map";
+                                return false;
+                            }
+                            g.con.push_back((int)(c.word | ((unsigned)col << AX_COL_SHIFT)));
+                        }
+                    }
+                g.ptr.push_back((int)g.con.size());
+            }
+            put_gather(im, g, o.Ax);
+        }
+        {
+            // r_nl is indexed by row as well (full CSR): r[row] = b[row] + nonlinear rhs terms
+            GatherBuild g;
+            g.ptr.push_back(0);
+            for (int row = 0; row < m.n; ++row) {
+                g.dst.push_back(row);
+                for (const Con &c : m.b)
+                    if (c.phase == NL && c.dst == row) g.con.push_back((int)c.word);
+                g.ptr.push_back((int)g.con.size());
+            }
+            put_gather(im, g, o.r_nl);
+        }
         {
             // f_nl is indexed by row: a full CSR over all n rows (rows without device currents are empty)
             GatherBuild g;

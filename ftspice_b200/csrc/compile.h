@@ -22,7 +22,7 @@ struct GatherOff {
 struct ModeOff {
     int n = 0, nv = 0, ni = 0, n_nl = 0, n_gfun = 0;
     int cls = 0, nl = 0;
-    GatherOff A_lin, A_dyn, J_nl, b_all, r_nl, f_nl;
+    GatherOff A_lin, A_dyn, J_nl, b_all, r_nl, f_nl, J_full, Ax;
 };
 
 struct Compiled {
@@ -37,7 +37,7 @@ struct Compiled {
     const std::vector<int> &ints() const;
 };
 
-bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start, const int *row_class, Compiled &out,
-                     std::string &err);
+bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start, const int *row_class, int ld_min,
+                     Compiled &out, std::string &err);
 
 } // namespace ftsb

@@ -52,6 +52,11 @@ struct RunArgs {
     double *t_out;
     long long *n_rec;
     double *x_final;
+    // .tran of the small-circuit kernels: start-up solution of a previous .op launch
+    const double *x_start;   // [batch][n_start]
+    const int *start_status; // [batch]
+    int n_start;
+    int pad3;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -189,12 +194,28 @@ struct CtaTeam {
     }
 };
 
-// per-instance working set
-struct Ws {
-    double *A, *J, *b, *r, *x, *xn, *xp, *val, *state, *ring, *prev;
-    int *piv;
+// per-instance working set.  Vec<S> is a strided view: S = 1 for team kernels (an instance's data is contiguous),
+// S = 32 for the thread-per-instance kernels (element e of lane t lives at word e*32 + t: every warp access is
+// bank-conflict free whatever per-thread element each lane touches).
+template <int S>
+struct Vec {
+    double *p;
+    __device__ __forceinline__ double &operator[](int i) const { return p[i * S]; }
+    __device__ __forceinline__ Vec operator+(int off) const { return Vec{p + off * S}; }
+    __device__ __forceinline__ explicit operator bool() const { return p != nullptr; }
+};
+template <int S>
+struct IVec {
+    int *p;
+    __device__ __forceinline__ int &operator[](int i) const { return p[i * S]; }
+};
+template <int S>
+struct WsT {
+    Vec<S> A, J, b, r, x, xn, xp, val, state, ring, prev;
+    IVec<S> piv;
     int ld;
 };
+using Ws = WsT<1>;
 
 struct Counters {
     unsigned long long c[6];
@@ -207,12 +228,13 @@ struct Counters {
 // ---------------------------------------------------------------------------------------------------------
 // gather-based assembly (no atomics: one thread owns one destination entry)
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ __forceinline__ void gather(const Team &tm, const Gather &g, double *out, const double *base,
-                                       const double *val)
+// ld > 0: the destinations are matrix entries (row | col << 16) of a column-major matrix with that leading dimension
+template <class Team, class V>
+__device__ __forceinline__ void gather(const Team &tm, const Gather &g, V out, V base, V val, int ld = 0)
 {
     for (int d = tm.rank; d < g.n_dst; d += tm.size()) {
         int off = __ldg(&g.dst[d]);
+        if (ld) off = (off >> 16) * ld + (off & 0xffff);
         double acc = base ? base[off] : 0.0;
         int c0 = __ldg(&g.ptr[d]), c1 = __ldg(&g.ptr[d + 1]);
         for (int c = c0; c < c1; ++c) {
@@ -252,12 +274,17 @@ __device__ __forceinline__ double spice_fn_eval(int kind, const double *p, doubl
 // nonlinear devices: one thread evaluates one device at x and fills its slots (conductances, equivalent
 // currents, terminal currents).  Returns per-thread (#non-finite g functions) | (panic << 20).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double xat(const double *x, int i) { return i >= 0 ? x[i] : 0.0; }
+template <class V>
+__device__ __forceinline__ double xat(V x, int i)
+{
+    return i >= 0 ? x[i] : 0.0;
+}
 
-__device__ __forceinline__ int eval_device(const int *d, const double *x, double *val)
+template <class V>
+__device__ __forceinline__ int eval_device(const int *d, V x, V val)
 {
     const int kind = d[0];
-    double *s = val + d[4];
+    const V s = val + d[4];
     if (kind == K_D) { // src/device/diode/model.rs:7-22
         const double ISAT = 1.0e-12, NVT = 1.0 * 26e-3;
         double vd = xat(x, d[1]) - xat(x, d[2]);
@@ -350,8 +377,8 @@ __device__ __forceinline__ int eval_device(const int *d, const double *x, double
 }
 
 // evaluates every nonlinear device at x; returns team-wide nbad | panic<<20
-template <class Team>
-__device__ __forceinline__ int eval_nl(const Team &tm, const ModeProg &M, const double *x, double *val)
+template <class Team, class V>
+__device__ __forceinline__ int eval_nl(const Team &tm, const ModeProg &M, V x, V val)
 {
     if (M.n_nl == 0) return 0;
     int acc = 0;
@@ -369,9 +396,9 @@ __device__ __forceinline__ int eval_nl(const Team &tm, const ModeProg &M, const 
 // ---------------------------------------------------------------------------------------------------------
 // residual f = A x + H g(x) - b and its class norms sqrt(sum f^2)/len  (mna.rs:25-29, node_vec_norm.rs:12-33)
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ __forceinline__ void resid_norms(const Team &tm, const ModeProg &M, const Ws &w, const double *x, int nbad,
-                                            double &nv, double &ni)
+template <class Team, class W, class V>
+__device__ __forceinline__ void resid_norms(const Team &tm, const ModeProg &M, const W &w, V x, int nbad, double &nv,
+                                            double &ni)
 {
     const int n = M.n, ld = w.ld;
     double sv = 0.0, si = 0.0;
@@ -403,8 +430,8 @@ __device__ __forceinline__ void resid_norms(const Team &tm, const ModeProg &M, c
     ni = sqrt(si) / (double)M.ni;
 }
 
-template <class Team>
-__device__ __forceinline__ void vec_norms(const Team &tm, const ModeProg &M, const double *v, double &nv, double &ni)
+template <class Team, class V>
+__device__ __forceinline__ void vec_norms(const Team &tm, const ModeProg &M, V v, double &nv, double &ni)
 {
     double sv = 0.0, si = 0.0;
     for (int i = tm.rank; i < M.n; i += tm.size()) {
@@ -424,8 +451,8 @@ __device__ __forceinline__ void vec_norms(const Team &tm, const ModeProg &M, con
 // Rows are not moved: each row carries its current *position*; the pivot is the candidate with the largest
 // |a| and, among equals, the smallest position — the reference's "first strictly larger" rule.
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ __forceinline__ void lu_factor(const Team &tm, int n, int ld, double *J, int *piv, int &mypos)
+template <class Team, class V, class IV>
+__device__ __forceinline__ void lu_factor(const Team &tm, int n, int ld, V J, IV piv, int &mypos)
 {
     const int r = tm.rank;
     const bool have = r < n;
@@ -461,9 +488,8 @@ __device__ __forceinline__ void lu_factor(const Team &tm, int n, int ld, double 
 }
 
 // forward + backward substitution with the stored multipliers; rhs in w (by row, destroyed), solution in xout
-template <class Team>
-__device__ __forceinline__ void lu_solve(const Team &tm, int n, int ld, const double *J, const int *piv, int mypos,
-                                         double *y, double *xout)
+template <class Team, class V, class IV>
+__device__ __forceinline__ void lu_solve(const Team &tm, int n, int ld, V J, IV piv, int mypos, V y, V xout)
 {
     const int r = tm.rank;
     const bool have = r < n;
@@ -485,13 +511,31 @@ __device__ __forceinline__ void lu_solve(const Team &tm, int n, int ld, const do
 // damped Newton (newtons_method.rs:19-71).  Returns n_iters >= 0, or -status.
 // A, b hold the linear part (incl. companions); val holds device values at x on entry? No: evaluated here.
 // ---------------------------------------------------------------------------------------------------------
-struct NewtonState {
-    bool jvalid; // J holds a valid factorisation of the current A (linear circuits only)
-    int mypos;   // this thread's row position in that factorisation
+// A *solver* policy provides State (what persists between Newton calls: the cached factorisation of a linear
+// circuit) and newton().  SmemSolver: generic, matrix in shared (or global) memory, one thread per row.
+template <class Team>
+struct SmemSolver {
+    struct State {
+        bool jvalid; // J holds a valid factorisation of the current A (linear circuits only)
+        int mypos;   // this thread's row position in that factorisation
+        __device__ State() : jvalid(false), mypos(0) {}
+    };
+    // called by the analysis drivers whenever the matrix A has been rebuilt
+    static constexpr bool kHasA = true; // keeps the assembled linear part A in memory
+    static constexpr bool kHasB = true; // ... and its right-hand side b
+    static constexpr bool kExternalStartup = false; // .tran runs its start-up .op itself
+    template <class W>
+    static __device__ __forceinline__ void matrix_changed(const Team &, const ModeProg &, const W &, State &ns)
+    {
+        ns.jvalid = false;
+    }
+    template <class W>
+    static __device__ int newton(const Team &tm, const ModeProg &M, const W &w, State &ns, Counters &cn, int skip);
 };
 
 template <class Team>
-__device__ int newton(const Team &tm, const ModeProg &M, const Ws &w, NewtonState &ns, Counters &cn, int skip)
+template <class W>
+__device__ int SmemSolver<Team>::newton(const Team &tm, const ModeProg &M, const W &w, State &ns, Counters &cn, int skip)
 {
     const int n = M.n, ld = w.ld;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -513,15 +557,22 @@ __device__ int newton(const Team &tm, const ModeProg &M, const Ws &w, NewtonStat
             for (int c = 0; c < n; ++c)
                 for (int i = tm.rank; i < n; i += tm.size()) w.J[c * ld + i] = w.A[c * ld + i];
             tm.sync();
-            gather(tm, M.J_nl, w.J, w.J, w.val);
+            gather(tm, M.J_nl, w.J, w.J, w.val, ld);
             lu_factor(tm, n, ld, w.J, w.piv, ns.mypos);
             ns.jvalid = linear;
             cn.c[CN_FACTOR]++;
         }
         if (!(linear && skip && xp_ready)) {
-            for (int i = tm.rank; i < n; i += tm.size()) w.r[i] = w.b[i];
-            tm.sync();
-            gather(tm, M.r_nl, w.r, w.r, w.val);
+            for (int i = tm.rank; i < n; i += tm.size()) { // r = b + nonlinear rhs (row-indexed map)
+                double acc = w.b[i];
+                int c0 = __ldg(&M.r_nl.ptr[i]), c1 = __ldg(&M.r_nl.ptr[i + 1]);
+                for (int c = c0; c < c1; ++c) {
+                    unsigned wd = (unsigned)__ldg(&M.r_nl.con[c]);
+                    double v = w.val[wd & ~CON_NEG];
+                    acc += (wd & CON_NEG) ? -v : v;
+                }
+                w.r[i] = acc;
+            }
             lu_solve(tm, n, ld, w.J, w.piv, ns.mypos, w.r, w.xp);
             xp_ready = true;
             cn.c[CN_SOLVE]++;
@@ -566,8 +617,8 @@ __device__ int newton(const Team &tm, const ModeProg &M, const Ws &w, NewtonStat
 // per-instance set-up shared by the three analyses: constant slot, resistor conductances, source values at
 // t = 0 (Engine::new evaluates waveforms at 0, src/engine.rs:47-51)
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ void load_instance(const Team &tm, const RunArgs &a, const Ws &w, long long inst)
+template <class Team, class W>
+__device__ __forceinline__ void load_instance(const Team &tm, const RunArgs &a, const W &w, long long inst)
 {
     const DevProg &P = a.prog;
     const double *vals = a.vals + inst * P.n_elems;
@@ -582,23 +633,26 @@ __device__ void load_instance(const Team &tm, const RunArgs &a, const Ws &w, lon
         int e = __ldg(&sd[0]), s = __ldg(&sd[1]), fk = __ldg(&sd[3]), fs = __ldg(&sd[4]);
         double v = fk != FN_NONE ? spice_fn_eval(fk, fn + fs * 7, 0.0) : vals[e];
         w.val[s] = v;
-        w.prev[3 * i] = v;     // value at t = 0
-        w.prev[3 * i + 1] = v; // value at the element's last evaluation before this step
-        w.prev[3 * i + 2] = v; // value at the current attempt
+        if (w.prev) { // source history, .tran only
+            w.prev[3 * i] = v;     // value at t = 0
+            w.prev[3 * i + 1] = v; // value at the element's last evaluation before this step
+            w.prev[3 * i + 2] = v; // value at the current attempt
+        }
     }
     tm.sync();
 }
 
-template <class Team>
-__device__ void build_linear(const Team &tm, const ModeProg &M, const Ws &w)
+template <class Team, class W>
+__device__ __forceinline__ void build_linear(const Team &tm, const ModeProg &M, const W &w, bool has_a, bool has_b)
 {
     const int n = M.n, ld = w.ld;
-    for (int c = 0; c < n; ++c)
-        for (int i = tm.rank; i < n; i += tm.size()) w.A[c * ld + i] = 0.0;
-    for (int i = tm.rank; i < n; i += tm.size()) w.b[i] = 0.0;
+    using V = decltype(w.b);
+    if (has_a)
+        for (int c = 0; c < n; ++c)
+            for (int i = tm.rank; i < n; i += tm.size()) w.A[c * ld + i] = 0.0;
     tm.sync();
-    gather(tm, M.A_lin, w.A, nullptr, w.val);
-    gather(tm, M.b_all, w.b, nullptr, w.val);
+    if (has_a) gather(tm, M.A_lin, w.A, V{nullptr}, w.val, ld);
+    if (has_b) gather(tm, M.b_all, w.b, V{nullptr}, w.val); // row-indexed: writes every row
     tm.sync();
 }
 
@@ -614,23 +668,23 @@ __device__ void flush_counters(const Team &tm, const RunArgs &a, const Counters 
 // ---------------------------------------------------------------------------------------------------------
 // Engine::run_op  (src/engine.rs:62-90) for one instance.  Leaves x (start-up numbering) in w.x.
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ int solve_op(const Team &tm, const RunArgs &a, const Ws &w, Counters &cn)
+template <class Team, class Solver, class W>
+__device__ __forceinline__ int solve_op(const Team &tm, const RunArgs &a, const W &w, Counters &cn)
 {
     const ModeProg &M = a.prog.op;
-    build_linear(tm, M, w);
+    build_linear(tm, M, w, Solver::kHasA, Solver::kHasB);
     for (int i = tm.rank; i < M.n; i += tm.size()) w.x[i] = 0.0;
     tm.sync();
-    NewtonState ns{false, 0};
-    return newton(tm, M, w, ns, cn, a.skip_refactor);
+    typename Solver::State ns;
+    Solver::matrix_changed(tm, M, w, ns);
+    return Solver::newton(tm, M, w, ns, cn, a.skip_refactor);
 }
 
-template <class Team>
-__device__ void run_op_instance(const Team &tm, const RunArgs &a, const Ws &w, long long inst)
+template <class Team, class Solver, class W>
+__device__ __forceinline__ void run_op_instance(const Team &tm, const RunArgs &a, const W &w, long long inst, Counters &cn)
 {
-    Counters cn;
     load_instance(tm, a, w, inst);
-    int r = solve_op(tm, a, w, cn);
+    int r = solve_op<Team, Solver, W>(tm, a, w, cn);
     const int n = a.prog.op.n;
     for (int i = tm.rank; i < n; i += tm.size()) a.x[inst * n + i] = w.x[i];
     if (tm.rank == 0) {
@@ -638,20 +692,18 @@ __device__ void run_op_instance(const Team &tm, const RunArgs &a, const Ws &w, l
         a.status[inst] = r >= 0 ? ST_OK : -r;
     }
     if (r >= 0) cn.c[CN_POINTS]++;
-    flush_counters(tm, a, cn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Engine::run_dc  (src/engine.rs:92-140): one warm-started chain per instance
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ void run_dc_instance(const Team &tm, const RunArgs &a, const Ws &w, long long inst)
+template <class Team, class Solver, class W>
+__device__ __forceinline__ void run_dc_instance(const Team &tm, const RunArgs &a, const W &w, long long inst, Counters &cn)
 {
-    Counters cn;
     const ModeProg &M = a.prog.dc;
     const int n = M.n;
     load_instance(tm, a, w, inst);
-    build_linear(tm, M, w);
+    build_linear(tm, M, w, Solver::kHasA, Solver::kHasB);
     for (int i = tm.rank; i < n; i += tm.size()) w.x[i] = 0.0;
     tm.sync();
     const double start = a.start[inst], stop = a.stop[inst], step = a.step[inst];
@@ -659,16 +711,17 @@ __device__ void run_dc_instance(const Team &tm, const RunArgs &a, const Ws &w, l
     long long count = cnt_d >= 0.0 ? (long long)cnt_d : 0;
     if (count > a.max_points) count = a.max_points;
     const int sweep_slot = __ldg(&a.prog.src[5 * a.sweep_src + 1]);
-    NewtonState ns{false, 0};
+    typename Solver::State ns;
+    Solver::matrix_changed(tm, M, w, ns);
     int status = ST_OK;
     long long k = 0;
     for (; k < count; ++k) {
         const double sv = start + step * (double)k;
         if (tm.rank == 0) w.val[sweep_slot] = sv;
         tm.sync();
-        gather(tm, M.b_all, w.b, nullptr, w.val);
+        if (Solver::kHasB) gather(tm, M.b_all, w.b, decltype(w.b){nullptr}, w.val);
         tm.sync();
-        int r = newton(tm, M, w, ns, cn, a.skip_refactor);
+        int r = Solver::newton(tm, M, w, ns, cn, a.skip_refactor);
         if (r < 0) { // `?` aborts the whole sweep (engine.rs:127)
             status = -r;
             break;
@@ -682,7 +735,6 @@ __device__ void run_dc_instance(const Team &tm, const RunArgs &a, const Ws &w, l
         a.points_done[inst] = k;
         a.status[inst] = status;
     }
-    flush_counters(tm, a, cn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -690,10 +742,9 @@ __device__ void run_dc_instance(const Team &tm, const RunArgs &a, const Ws &w, l
 // form of SURVEY.md App. D: companions frozen at the first attempt's h (Q10), x never restored (Q11),
 // current sources drift (Q9), PLTE over a ring of the last three accepted points.
 // ---------------------------------------------------------------------------------------------------------
-template <class Team>
-__device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w, long long inst)
+template <class Team, class Solver, class W>
+__device__ __forceinline__ void run_tran_instance(const Team &tm, const RunArgs &a, const W &w, long long inst, Counters &cn)
 {
-    Counters cn;
     const DevProg &P = a.prog;
     const ModeProg &M = P.tran;
     const int n = M.n, ld = w.ld;
@@ -705,7 +756,15 @@ __device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w,
     int status = ST_OK;
 
     // start-up solution: a full .op in the start-up numbering (engine.rs:158-161, Q13)
-    int r0 = solve_op(tm, a, w, cn);
+    int r0 = 0;
+    if constexpr (Solver::kExternalStartup) {
+        const int st0 = a.start_status[inst];
+        r0 = st0 == ST_OK ? 0 : -st0;
+        for (int i = tm.rank; i < n; i += tm.size()) w.x[i] = a.x_start[inst * a.n_start + i];
+        tm.sync();
+    } else {
+        r0 = solve_op<Team, Solver, W>(tm, a, w, cn);
+    }
     if (r0 < 0) {
         status = -r0;
     } else {
@@ -718,17 +777,20 @@ __device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w,
                 w.state[2 * i + 1] = 0.0;
             } else {
                 w.state[2 * i] = 0.0;
-                w.state[2 * i + 1] = w.x[br];
+                if constexpr (Solver::kExternalStartup)
+                    w.state[2 * i + 1] = a.x_start[inst * a.n_start + br];
+                else
+                    w.state[2 * i + 1] = w.x[br];
             }
         }
         tm.sync();
         // x (run numbering) is the prefix of the start-up x: nothing to move.  Linear part for .tran:
-        build_linear(tm, M, w);
+        build_linear(tm, M, w, Solver::kHasA, Solver::kHasB);
 
         double t = 0.0, h = 1e-18;
         double tr0 = 0.0, tr1 = 0.0, tr2 = 0.0; // times of the last three accepted records (oldest first)
         double hA = -1.0;                        // h the companions in A were built with
-        NewtonState ns{false, 0};
+        typename Solver::State ns;
         const double c3 = -1.0 / 12.0;
 
         while (t < a.t_stop && status == ST_OK) {
@@ -750,10 +812,10 @@ __device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w,
             }
             tm.sync();
             if (h_first != hA) {
-                gather(tm, M.A_dyn, w.A, nullptr, w.val);
+                if (Solver::kHasA) gather(tm, M.A_dyn, w.A, decltype(w.A){nullptr}, w.val, ld);
                 hA = h_first;
-                ns.jvalid = false;
                 tm.sync();
+                Solver::matrix_changed(tm, M, w, ns);
             }
             double next_h = h;
             bool accepted = false;
@@ -772,9 +834,9 @@ __device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w,
                     }
                 }
                 tm.sync();
-                gather(tm, M.b_all, w.b, nullptr, w.val);
+                if (Solver::kHasB) gather(tm, M.b_all, w.b, decltype(w.b){nullptr}, w.val);
                 tm.sync();
-                int r = newton(tm, M, w, ns, cn, a.skip_refactor);
+                int r = Solver::newton(tm, M, w, ns, cn, a.skip_refactor);
                 if (r == -ST_NOT_CONVERGED) {
                     h *= 0.5;
                     cn.c[CN_REJ_NEWTON]++;
@@ -882,7 +944,6 @@ __device__ void run_tran_instance(const Team &tm, const RunArgs &a, const Ws &w,
         a.n_rec[inst] = nrec;
         a.status[inst] = status;
     }
-    flush_counters(tm, a, cn);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -894,30 +955,30 @@ __device__ __forceinline__ Ws make_ws(const Layout &L, double *vec, double *mat,
 {
     Ws w;
     w.ld = L.ld;
-    w.b = vec + L.ob;
-    w.r = vec + L.orr;
-    w.x = vec + L.ox;
-    w.xn = vec + L.oxn;
-    w.xp = vec + L.oxp;
-    w.val = vec + L.oval;
-    w.state = vec + L.ostate;
-    w.ring = vec + L.oring;
-    w.prev = vec + L.oprev;
-    w.A = mat;
-    w.J = mat + L.mat_doubles;
-    w.piv = ints;
+    w.b.p = vec + L.ob;
+    w.r.p = vec + L.orr;
+    w.x.p = vec + L.ox;
+    w.xn.p = vec + L.oxn;
+    w.xp.p = vec + L.oxp;
+    w.val.p = vec + L.oval;
+    w.state.p = vec + L.ostate;
+    w.ring.p = vec + L.oring;
+    w.prev.p = vec + L.oprev;
+    w.A.p = mat;
+    w.J.p = mat + L.mat_doubles;
+    w.piv.p = ints;
     return w;
 }
 
-template <class Team, int AN>
-__device__ __forceinline__ void run_instance(const Team &tm, const RunArgs &a, const Ws &w, long long inst)
+template <class Team, class Solver, int AN, class W>
+__device__ __forceinline__ void run_instance(const Team &tm, const RunArgs &a, const W &w, long long inst, Counters &cn)
 {
     if (AN == AN_OP)
-        run_op_instance(tm, a, w, inst);
+        run_op_instance<Team, Solver, W>(tm, a, w, inst, cn);
     else if (AN == AN_DC)
-        run_dc_instance(tm, a, w, inst);
+        run_dc_instance<Team, Solver, W>(tm, a, w, inst, cn);
     else
-        run_tran_instance(tm, a, w, inst);
+        run_tran_instance<Team, Solver, W>(tm, a, w, inst, cn);
 }
 
 template <int G, int AN>
@@ -932,14 +993,16 @@ __global__ void __launch_bounds__(128) k_subwarp(const __grid_constant__ RunArgs
     double *mat = vec + L.doubles;
     int *ints = reinterpret_cast<int *>(mat + 2 * L.mat_doubles);
     Ws w = make_ws(L, vec, mat, ints);
+    Counters cn;
     for (;;) {
         long long inst = 0;
         if (tm.rank == 0) inst = (long long)atomicAdd(a.work, 1ULL);
         inst = tm.bcast_ll(inst);
         if (inst >= a.batch) break;
-        run_instance<SubWarp<G>, AN>(tm, a, w, inst);
+        run_instance<SubWarp<G>, SmemSolver<SubWarp<G>>, AN>(tm, a, w, inst, cn);
         tm.sync();
     }
+    flush_counters(tm, a, cn);
 }
 
 template <int AN>
@@ -953,14 +1016,16 @@ __global__ void k_cta(const __grid_constant__ RunArgs a)
     double *mat = L.mat_in_smem ? vec + L.doubles : a.scratch + (size_t)blockIdx.x * 2 * L.mat_doubles;
     int *ints = reinterpret_cast<int *>(vec + L.doubles + (L.mat_in_smem ? 2 * L.mat_doubles : 0));
     Ws w = make_ws(L, vec, mat, ints);
+    Counters cn;
     for (;;) {
         long long inst = 0;
         if (threadIdx.x == 0) inst = (long long)atomicAdd(a.work, 1ULL);
         inst = tm.bcast_ll(inst);
         if (inst >= a.batch) break;
-        run_instance<CtaTeam, AN>(tm, a, w, inst);
+        run_instance<CtaTeam, SmemSolver<CtaTeam>, AN>(tm, a, w, inst, cn);
         tm.sync();
     }
+    flush_counters(tm, a, cn);
 }
 
 } // namespace ftsb

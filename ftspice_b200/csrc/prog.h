@@ -36,7 +36,7 @@ constexpr unsigned CON_NEG = 0x80000000u; // contribution word = slot | (negativ
 
 // CSR gather map over destinations
 struct Gather {
-    const int *dst; // [n_dst] offset into the target array
+    const int *dst; // [n_dst] target: a row (vectors) or row | col << 16 (matrices; the kernel applies its own ld)
     const int *ptr; // [n_dst + 1]
     const int *con; // contribution words
     int n_dst;
@@ -56,10 +56,15 @@ struct ModeProg {
     Gather A_lin;   // A[dst] = sum of linear stamps                       (R, V, start-up L)
     Gather A_dyn;   // A[dst] = linear + companion stamps, dst touched by C/L (TRAN only)
     Gather J_nl;    // J[dst] = A[dst] + nonlinear stamps
-    Gather b_all;   // b[row] = linear + companion rhs
-    Gather r_nl;    // r[row] = b[row] + nonlinear rhs
-    Gather f_nl;    // (H g)[row] = sum of device currents
+    Gather b_all;   // b[row] = linear + companion rhs                    (row-indexed: ptr has n+1 entries)
+    Gather r_nl;    // r[row] = b[row] + nonlinear rhs                      (row-indexed)
+    Gather f_nl;    // (H g)[row] = sum of device currents                  (row-indexed)
+    // thread-per-instance kernels keep neither A nor b in memory:
+    Gather J_full;  // J[dst] = linear + companion + nonlinear stamps, every structurally non-zero entry
+    Gather Ax;      // row-indexed; con = slot | sign | col << AX_COL_SHIFT: (A x)[row] = sum of +-val[slot] * x[col]
 };
+constexpr int AX_COL_SHIFT = 20;
+constexpr unsigned AX_SLOT_MASK = (1u << AX_COL_SHIFT) - 1u;
 
 // per-instance working-set layout (offsets in doubles from the instance base)
 struct Layout {

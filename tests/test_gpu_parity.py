@@ -312,3 +312,61 @@ def test_api_errors():
     with pytest.raises(capi.FtsbError) as ei:
         be.run_dc(circ.elem_index("R12"), 0.0, 1.0, 0.1)  # not a source
     assert ei.value.code == capi.E_ARG
+
+
+@pytest.mark.parametrize("name,an", [("proj2", "dc"), ("proj3", "tran"), ("rc_pulse", "tran"), ("npn_test", "op"),
+                                      ("proj1", "op"), ("v_divider_sweep", "dc")])
+def test_thread_kernel_equals_generic_kernel_bitwise(name, an):
+    """The thread-per-instance solver and the generic team solver execute the same solution-path arithmetic in the
+    same order (no FMA contraction in either): every output bit must agree."""
+    circ = load(name)
+    outs = []
+    for generic in (0, 1):
+        be = BatchEngine(circ)
+        be.set_option("force_generic", generic)
+        vals, fns = nl.monte_carlo(circ, 40)
+        be.set_params(vals, fns)
+        if an == "op":
+            r = be.run_op()
+            outs.append((be.variant, r.status, r.n_iters, r.x))
+        elif an == "dc":
+            d = circ.command("dc")
+            r = be.run_dc(d.source, d.start, d.stop, d.step)
+            outs.append((be.variant, r.status, r.points_done, r.n_iters, r.x))
+        else:
+            t = circ.command("tran")
+            r = be.run_tran(t.stop, t.step, capacity=700)
+            outs.append((be.variant, r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final))
+    assert outs[0][0].startswith(("lanes", "sync")) and outs[1][0].startswith("warp"), (outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("name,an", [("proj2", "dc"), ("npn_test", "op"), ("v_divider_sweep", "dc"), ("nmos_test", "op"),
+                                      ("proj3", "tran"), ("rl", "tran")])
+@pytest.mark.parametrize("lanes", [1, 2, 4])
+def test_lane_counts_agree_bitwise(name, an, lanes):
+    """Small-circuit kernels with 1, 2 or 4 lanes per instance (where built; others fall back to the default) against
+    the generic team kernel: every bit must agree.  Ragged batch (not a multiple of the instances per warp)."""
+    circ = load(name)
+    outs = []
+    for generic in (0, 1):
+        be = BatchEngine(circ)
+        be.set_option("force_generic", generic)
+        be.set_option("lanes", lanes)
+        vals, fns = nl.monte_carlo(circ, 75)
+        be.set_params(vals, fns)
+        if an == "op":
+            r = be.run_op()
+            outs.append((r.status, r.n_iters, r.x, be.counters()["newton_iters"]))
+        elif an == "dc":
+            d = circ.command("dc")
+            r = be.run_dc(d.source, d.start, d.stop, d.step)
+            outs.append((r.status, r.points_done, r.n_iters, r.x, be.counters()["newton_iters"]))
+        else:
+            t = circ.command("tran")
+            r = be.run_tran(t.stop, t.step, capacity=400)
+            c = be.counters()
+            outs.append((r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"]))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b, equal_nan=True)
