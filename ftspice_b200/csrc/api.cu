@@ -12,6 +12,7 @@
 #include "../../include/ftsb.h"
 #include "compile.h"
 #include "solver_lanes.cuh"
+#include "solver_warp.cuh"
 
 using namespace ftsb;
 
@@ -205,6 +206,48 @@ int plan_lanes(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     return 0;
 }
 
+// warp-per-instance kernels (solver_warp.cuh): 16 < n_start <= 96.  Returns 0 when chosen.
+int plan_warp(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
+{
+    const int n_start = std::max(c->comp.n_start, 1);
+    const int n = an == AN_OP ? n_start : c->comp.n_run;
+    if (n_start > 96 || n < 1) return 1;
+    const int rpt = (n + 31) / 32;
+    KernelFn fn = warp_kernel(rpt, an);
+    if (!fn) return 1;
+    const WarpLayout T = warp_layout(n, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    const size_t smem = (T.bytes + 15) & ~(size_t)15;
+    if (smem > c->smem_optin) return 1;
+    if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    pl.fn = fn;
+    pl.g = 32;
+    pl.block = 32;
+    pl.smem = smem;
+    pl.lay = c->comp.lay;
+    pl.lay.mat_in_smem = 1;
+    pl.lay.bytes = (int)smem;
+    pl.scratch_bytes = 0;
+    pl.lanes = true; // .tran takes its start-up solution from a separate .op launch
+    pl.grid = (int)std::max(1LL, std::min((long long)batch, (long long)occ * c->sm_count));
+    c->variant = "warp" + std::to_string(rpt) + "r_n" + std::to_string(n) + "/occ" + std::to_string(occ);
+    return 0;
+}
+
+int plan_small(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
+{
+    if (c->force_generic || c->force_cta) return 1;
+    if (std::max(c->comp.n_start, 1) <= 16) return plan_lanes(c, an, batch, pl);
+    return plan_warp(c, an, batch, pl);
+}
+
 int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
 {
     const int n = std::max(c->comp.n_start, 1);
@@ -214,7 +257,7 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     const size_t int_bytes = (size_t)L.ints * 4;
     int g = n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : n <= 32 ? 32 : 0;
     if (c->force_cta) g = 0;
-    if (g && !c->force_generic && plan_lanes(c, an, batch, pl) == 0) return 0;
+    if (plan_small(c, an, batch, pl) == 0) return 0;
     if (g) {
         size_t per = (vec_bytes + mat_bytes + int_bytes + 15) & ~(size_t)15;
         int teams = 128 / g;
@@ -285,7 +328,7 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
         // start-up solutions (engine.rs:158-161) by the .op kernel, kept on the device for the .tran kernel
         const std::string tran_variant = c->variant;
         LaunchPlan po;
-        if (plan_lanes(c, AN_OP, a.batch, po) != 0) return fail(c, FTSB_E_UNSUPPORTED, "no start-up kernel for this circuit");
+        if (plan_small(c, AN_OP, a.batch, po) != 0) return fail(c, FTSB_E_UNSUPPORTED, "no start-up kernel for this circuit");
         const int ns = std::max(c->comp.n_start, 1);
         FTSB_CUDA(c, c->s_x.ensure((size_t)a.batch * ns * 8));
         FTSB_CUDA(c, c->s_it.ensure((size_t)a.batch * 4));

@@ -1,4 +1,4 @@
-// kern_lanes_e.cu — instantiations of the small-circuit kernels (solver_lanes.cuh): (lanes per instance, n) = [(1, 14), (2, 14), (1, 5), (4, 5)]
+// kern_lanes_e.cu — instantiations of the small-circuit kernels (solver_lanes.cuh): (lanes per instance, n) = [(1, 14), (2, 14), (1, 5), (4, 5), (8, 14), (8, 5)]
 // n is the exact unknown count of the analysis mode: .op uses n_start, .dc and .tran use n_run.
 #include "solver_lanes.cuh"
 
@@ -14,6 +14,8 @@ KernelFn lanes_kernel_e(int g, int nc, int an)
     if (g == 2 && nc == 14) return pick_an<2, 14>(an);
     if (g == 1 && nc == 5) return pick_an<1, 5>(an);
     if (g == 4 && nc == 5) return pick_an<4, 5>(an);
+    if (g == 8 && nc == 14) return pick_an<8, 14>(an);
+    if (g == 8 && nc == 5) return pick_an<8, 5>(an);
     return nullptr;
 }
 } // namespace ftsb

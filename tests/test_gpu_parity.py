@@ -370,3 +370,35 @@ def test_lane_counts_agree_bitwise(name, an, lanes):
             outs.append((r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"]))
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("which", ["ladder24", "ladder64", "inverter40", "ladder30_op"])
+def test_warp_kernel_equals_generic_kernel_bitwise(which):
+    """Mid-size circuits (16 < n <= 96): the warp-per-instance kernels (1-3 rows per lane, start-up .op as its own
+    launch) against the generic team / CTA kernels: every bit must agree."""
+    if which == "inverter40":
+        circ = nl.load(nl.inverter_chain_netlist(40, stop="2n", step="50p"))
+    elif which == "ladder30_op":
+        circ = nl.load(nl.ladder_netlist(30, stop="30n", step="1n") .replace(".TRAN 30n 1n", ".OP"))
+    else:
+        circ = nl.load(nl.ladder_netlist(int(which[6:]), "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )", stop="40n", step="1n"))
+    B = 5
+    vals, fns = nl.monte_carlo(circ, B)
+    outs = []
+    for generic in (0, 1):
+        be = BatchEngine(circ)
+        be.set_option("force_generic", generic)
+        be.set_params(vals, fns)
+        if circ.command("tran"):
+            t = circ.command("tran")
+            r = be.run_tran(t.stop, t.step, capacity=300)
+            c = be.counters()
+            outs.append((be.variant, r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"],
+                         c["rej_newton"]))
+        else:
+            r = be.run_op()
+            outs.append((be.variant, r.status, r.n_iters, r.x))
+    assert outs[0][0].startswith("warp") and "r_n" in outs[0][0], outs[0][0]
+    assert not ("r_n" in outs[1][0]), outs[1][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a, b, equal_nan=True)
