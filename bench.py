@@ -221,7 +221,8 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or {"op": 8192, "dc": 256, "tran": 16}[wl["kind"]]
+        # bounded sample of the same workload per step: the full batch for .op (a few hundred ms on a multi-core host)
+        sample = args.cpu_sample or {"op": wl["batch"], "dc": min(wl["batch"], 1024), "tran": 16}[wl["kind"]]
         if wl["kind"] == "tran" and not args.tran_stop:
             wl["stop"] = wl["stop"] / 20.0  # bounded: 1/20 of the time span per step (about 500 accepted steps)
         for _ in range(max(args.warmup, 0)):
