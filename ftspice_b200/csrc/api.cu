@@ -64,7 +64,10 @@ struct ftsb_circuit {
     int skip_refactor = 1;
     int force_cta = 0;
     int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
-    int lanes = 0;         // >0: lanes per instance requested for the small-circuit kernels (if built)
+    int lanes = 0;         // >0: lanes per instance requested for the dense small-circuit kernels (if built)
+    int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
+                           // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
+                           // 2-3 warps per SM in shared memory and is latency bound)
 };
 
 #define FTSB_CUDA(c, call)                                                                        \
@@ -154,30 +157,40 @@ struct LaunchPlan {
     bool lanes = false; // small-circuit kernel: .tran needs the start-up .op as a separate launch
 };
 
-// small-circuit kernels (solver_lanes.cuh): n <= 16, G lanes per instance.  Returns 0 when chosen.
-KernelFn find_lanes_kernel(int g, int nc, int an)
+// small-circuit kernels (solver_lanes.cuh): n <= 16.  sp = 1: zero-skipping elimination, one thread per instance;
+// sp = 0: dense elimination, G lanes per instance.
+KernelFn find_lanes_kernel(int g, int nc, int an, int sp)
 {
-    KernelFn fn = lanes_kernel_a(g, nc, an);
-    if (!fn) fn = lanes_kernel_b(g, nc, an);
-    if (!fn) fn = lanes_kernel_c(g, nc, an);
-    if (!fn) fn = lanes_kernel_d(g, nc, an);
-    if (!fn) fn = lanes_kernel_e(g, nc, an);
-    return fn;
+    KernelFn (*const tab[])(int, int, int, int) = {lanes_kernel_a,  lanes_kernel_b,  lanes_kernel_c,  lanes_kernel_d, lanes_kernel_e,
+                                                    lanes_kernel_s1, lanes_kernel_s2, lanes_kernel_s3, lanes_kernel_s4};
+    for (auto f : tab)
+        if (KernelFn fn = f(g, nc, an, sp)) return fn;
+    return nullptr;
 }
 
+// Returns 0 when a small-circuit kernel was chosen.
 int plan_lanes(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
 {
     const int n_start = std::max(c->comp.n_start, 1);
     const int n = an == AN_OP ? n_start : c->comp.n_run; // exact unknown count of the analysis mode
     if (n_start > 16 || n < 1) return 1;
-    int g = c->lanes > 0 ? c->lanes : (n <= 4 ? 1 : n <= 8 ? 2 : 4);
-    KernelFn fn = find_lanes_kernel(g, n, an);
-    if (!fn && c->lanes > 0) { // requested lane count not built: fall back to the default
-        g = n <= 4 ? 1 : n <= 8 ? 2 : 4;
-        fn = find_lanes_kernel(g, n, an);
+    int g = 1, sp = 0;
+    KernelFn fn = nullptr;
+    if (c->sparse && c->lanes <= 0) { // opt-in: zero-skipping, thread per instance
+        sp = 1;
+        fn = find_lanes_kernel(1, n, an, 1);
+    }
+    if (!fn) {
+        sp = 0;
+        g = c->lanes > 0 ? c->lanes : (n <= 4 ? 1 : n <= 8 ? 2 : 4);
+        fn = find_lanes_kernel(g, n, an, 0);
+        if (!fn && c->lanes > 0) { // requested lane count not built: fall back to the default
+            g = n <= 4 ? 1 : n <= 8 ? 2 : 4;
+            fn = find_lanes_kernel(g, n, an, 0);
+        }
     }
     if (!fn) return 1;
-    const LaneLayout T = lane_layout(n, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    const LaneLayout T = lane_layout(n, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, sp != 0);
     const size_t smem = (size_t)T.doubles * (32 / g) * 8;
     if (smem > c->smem_optin) return 1;
     if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -201,8 +214,8 @@ int plan_lanes(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     const int per_warp = 32 / g;
     long long need = (batch + per_warp - 1) / per_warp;
     pl.grid = (int)std::max(1LL, std::min(need, (long long)occ * c->sm_count));
-    c->variant = std::string(an == AN_TRAN ? "lanes" : "sync") + std::to_string(g) + "n" + std::to_string(n) + "/occ" +
-                 std::to_string(occ);
+    c->variant = std::string(sp ? "zskip" : an == AN_TRAN ? "lanes" : "sync") + std::to_string(g) + "n" + std::to_string(n) +
+                 "/occ" + std::to_string(occ);
     return 0;
 }
 
@@ -497,6 +510,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->force_generic = value ? 1 : 0;
     else if (!strcmp(name, "lanes"))
         c->lanes = (int)value;
+    else if (!strcmp(name, "sparse"))
+        c->sparse = value ? 1 : 0;
     else
         return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
     return 0;

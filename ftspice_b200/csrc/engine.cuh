@@ -214,6 +214,7 @@ struct WsT {
     Vec<S> A, J, b, r, x, xn, xp, val, state, ring, prev;
     IVec<S> piv;
     int ld;
+    const int *aux; // zero-skipping lane kernels: the static structure words (shared by the block)
 };
 using Ws = WsT<1>;
 

@@ -88,11 +88,202 @@ struct LaneTeam {
     __device__ long long bcast_ll(long long v) const { return G > 1 ? __shfl_sync(mask, v, slot) : v; }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Zero-skipping elimination for the thread-per-instance kernels (G = 1).
+//
+// MNA matrices are sparse (C2: 40 structural non-zeros of 196; 819 dense element updates per factorisation, 49 of
+// them on non-zeros).  The reference's dense elimination (gauss_lu.rs:29-42) spends the rest on `a - 0*p`, which
+// leaves `a` unchanged, so skipping those updates reproduces its result (up to the sign of a zero) as long as every
+// value involved is finite.  The structure is tracked at run time, per instance, because partial pivoting is value
+// dependent: one 32-bit word per index i = rowmask(i) | colmask(i) << 16 (which columns row i holds; which rows
+// hold column i).  J stays in its dense column-major slots, but entries outside the masks are never read, so the
+// matrix is not zero-filled before assembly.  Same pivot rule (first position with the strictly largest |a|), same
+// reciprocal scaling, same separate multiply / subtract, same update order as the dense path.
+// A factorisation that meets a zero, infinite or NaN pivot candidate, or a non-finite solution component, returns
+// false: the caller then repeats it with the dense arithmetic (0*inf = NaN poisoning and all), so the observable
+// behaviour in those cases is the reference's too.
+// ---------------------------------------------------------------------------------------------------------
+template <int NC>
+struct SparseLU {
+    static_assert(NC <= 16, "masks are 16 bits wide");
+    static constexpr int TS = 32;
+    static constexpr unsigned FULL = (1u << NC) - 1u;
+    static __device__ __forceinline__ int nib_get(unsigned long long p, int i) { return (int)((p >> (4 * i)) & 15ull); }
+    static __device__ __forceinline__ unsigned long long nib_set(unsigned long long p, int i, int r)
+    {
+        return (p & ~(15ull << (4 * i))) | ((unsigned long long)r << (4 * i));
+    }
+    static __device__ __forceinline__ double &at(double *Jp, int r, int j) { return Jp[(j * NC + r) * TS]; }
+
+    // mk[i], i < NC: structure words (reset from the static pattern mk0); mk[NC + k]: rows eliminated at step k
+    // (low half) and rows of U holding column k (high half), for the substitutions
+    static __device__ __forceinline__ bool factor(double *__restrict__ Jp, double *__restrict__ yp, int *__restrict__ mk,
+                                                  const int *__restrict__ mk0, unsigned long long &perm)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) mk[i * TS] = mk0[i];
+        perm = 0xfedcba9876543210ull;                    // position -> row
+        unsigned long long posn = 0xfedcba9876543210ull; // row -> position
+        unsigned active = FULL;                          // rows not yet chosen as a pivot
+        bool ok = true;
+        for (int k = 0; k < NC; ++k) {
+            const unsigned colk = ((unsigned)mk[k * TS] >> 16) & FULL;
+            const unsigned cand = colk & active;
+            // pivot: first position with the strictly largest |a| (gauss_lu.rs:6-16); structural zeros cannot win
+            double vmax = -1.0;
+            int P = nib_get(perm, k), ppos = k;
+            for (unsigned c = cand; c; c &= c - 1u) {
+                const int r = __ffs((int)c) - 1;
+                const double v = fabs(at(Jp, r, k));
+                const int p = nib_get(posn, r);
+                ok = ok && (v < INF);
+                if (v > vmax || (v == vmax && p < ppos)) {
+                    vmax = v;
+                    P = r;
+                    ppos = p;
+                }
+            }
+            ok = ok && (vmax > 0.0);
+            if (!ok) break;
+            const int rk = nib_get(perm, k); // row swap (:19-27)
+            perm = nib_set(nib_set(perm, ppos, rk), k, P);
+            posn = nib_set(nib_set(posn, rk, ppos), P, k);
+            const unsigned done = FULL & ~active;
+            active &= ~(1u << P);
+            const double alpha = 1.0 / at(Jp, P, k); // (:31)
+            const double yk = yp[P * TS];
+            const unsigned cols = (unsigned)mk[P * TS] & FULL & ~((2u << k) - 1u); // pivot row, columns > k
+            unsigned lrows = 0;
+            for (unsigned c = cand & active; c; c &= c - 1u) {
+                const int r = __ffs((int)c) - 1;
+                const double a = at(Jp, r, k);
+                const double m = alpha * a;
+                at(Jp, r, k) = m;
+                if (a != 0.0) {
+                    lrows |= 1u << r;
+                    yp[r * TS] = yp[r * TS] - m * yk; // (:40)
+                    const unsigned w = (unsigned)mk[r * TS];
+                    mk[r * TS] = (int)(w | cols);
+                    for (unsigned cc = cols; cc; cc &= cc - 1u) {
+                        const int j = __ffs((int)cc) - 1;
+                        const double t = m * at(Jp, P, j);
+                        if ((w >> j) & 1u) {
+                            at(Jp, r, j) = at(Jp, r, j) - t; // (:35-39)
+                        } else { // fill-in: the dense entry was +0.0
+                            at(Jp, r, j) = 0.0 - t;
+                            mk[j * TS] = (int)((unsigned)mk[j * TS] | (1u << (16 + r)));
+                        }
+                    }
+                }
+            }
+            mk[(NC + k) * TS] = (int)(lrows | ((colk & done) << 16));
+        }
+        return ok;
+    }
+
+    // new right-hand side through the stored multipliers
+    static __device__ __forceinline__ void forward(const double *__restrict__ Jp, double *__restrict__ yp,
+                                                   const int *__restrict__ mk, unsigned long long perm)
+    {
+        for (int k = 0; k < NC - 1; ++k) {
+            const double yk = yp[nib_get(perm, k) * TS];
+            for (unsigned c = (unsigned)mk[(NC + k) * TS] & FULL; c; c &= c - 1u) {
+                const int r = __ffs((int)c) - 1;
+                yp[r * TS] = yp[r * TS] - Jp[(k * NC + r) * TS] * yk;
+            }
+        }
+    }
+
+    // gauss_lu.rs:44-53; false when a solution component is not finite
+    static __device__ __forceinline__ bool backward(const double *__restrict__ Jp, double *__restrict__ yp,
+                                                    double *__restrict__ xp, const int *__restrict__ mk,
+                                                    unsigned long long perm)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        bool ok = true;
+        for (int i = NC - 1; i >= 0; --i) {
+            const int ri = nib_get(perm, i);
+            const double xi = yp[ri * TS] / Jp[(i * NC + ri) * TS];
+            xp[i * TS] = xi;
+            ok = ok && (fabs(xi) < INF);
+            for (unsigned c = ((unsigned)mk[(NC + i) * TS] >> 16) & FULL; c; c &= c - 1u) {
+                const int r = __ffs((int)c) - 1;
+                yp[r * TS] = yp[r * TS] - xi * Jp[(i * NC + r) * TS];
+            }
+        }
+        return ok;
+    }
+};
+
+// Dense elimination with run-time loops (compact code): the exact-arithmetic path the zero-skipping solver falls
+// back to.  Same operations in the same order as LaneSolver::factor / forward / backward with G = 1.
+template <int NC>
+struct DenseDyn {
+    static constexpr int TS = 32;
+    static __device__ __forceinline__ int nib_get(unsigned long long p, int i) { return (int)((p >> (4 * i)) & 15ull); }
+    static __device__ __forceinline__ unsigned long long nib_set(unsigned long long p, int i, int r)
+    {
+        return (p & ~(15ull << (4 * i))) | ((unsigned long long)r << (4 * i));
+    }
+    static __device__ __noinline__ void factor(double *Jp, double *yp, unsigned long long &perm_out)
+    {
+        unsigned long long perm = 0xfedcba9876543210ull;
+        for (int k = 0; k < NC; ++k) {
+            int imax = k;
+            double vmax = fabs(Jp[(k * NC + nib_get(perm, k)) * TS]);
+            for (int i = k + 1; i < NC; ++i) {
+                const double v = fabs(Jp[(k * NC + nib_get(perm, i)) * TS]);
+                if (v > vmax) {
+                    vmax = v;
+                    imax = i;
+                }
+            }
+            const int rk = nib_get(perm, k), rp = nib_get(perm, imax);
+            perm = nib_set(nib_set(perm, imax, rk), k, rp);
+            const double alpha = 1.0 / Jp[(k * NC + rp) * TS];
+            const double yk = yp[rp * TS];
+            for (int i = k + 1; i < NC; ++i) {
+                const int r = nib_get(perm, i);
+                const double m = alpha * Jp[(k * NC + r) * TS];
+                Jp[(k * NC + r) * TS] = m;
+                for (int j = k + 1; j < NC; ++j) Jp[(j * NC + r) * TS] = Jp[(j * NC + r) * TS] - m * Jp[(j * NC + rp) * TS];
+                yp[r * TS] = yp[r * TS] - m * yk;
+            }
+        }
+        perm_out = perm;
+    }
+    static __device__ __noinline__ void forward(const double *Jp, double *yp, unsigned long long perm)
+    {
+        for (int k = 0; k < NC - 1; ++k) {
+            const double yk = yp[nib_get(perm, k) * TS];
+            for (int i = k + 1; i < NC; ++i) {
+                const int r = nib_get(perm, i);
+                yp[r * TS] = yp[r * TS] - Jp[(k * NC + r) * TS] * yk;
+            }
+        }
+    }
+    static __device__ __noinline__ void backward(const double *Jp, double *yp, double *xp, unsigned long long perm)
+    {
+        for (int i = NC - 1; i >= 0; --i) {
+            const int ri = nib_get(perm, i);
+            const double xi = yp[ri * TS] / Jp[(i * NC + ri) * TS];
+            xp[i * TS] = xi;
+            for (int j = i - 1; j >= 0; --j) {
+                const int rj = nib_get(perm, j);
+                yp[rj * TS] = yp[rj * TS] - xi * Jp[(i * NC + rj) * TS];
+            }
+        }
+    }
+};
+
 // N = the analysis mode's unknown count, known at compile time (= leading dimension of J): the statically unrolled
 // elimination has no run-time guards (a run-time `j < n` inside the unrolled code makes the compiler track the
 // validity of every cached pivot-row element with dozens of predicate instructions per load).
-template <int G, int NC>
+// SP: zero-skipping elimination (SparseLU above; G = 1 only).
+template <int G, int NC, bool SP = false>
 struct LaneSolver {
+    static_assert(!SP || G == 1, "the zero-skipping solver is thread-per-instance");
     using Team = LaneTeam<G>;
     static constexpr int TS = 32 / G; // element stride inside the warp's region
     static constexpr bool kHasA = false;
@@ -100,8 +291,9 @@ struct LaneSolver {
     static constexpr bool kExternalStartup = true; // .tran takes its start-up solution from a previous launch
     struct State {
         bool jvalid;             // J holds the factorisation of the current matrix (linear circuits only)
+        bool dense;              // SP: that factorisation was made by the dense fall-back (masks are not valid)
         unsigned long long perm; // row at position i in nibble i (n <= 16); identical in all lanes of the team
-        __device__ State() : jvalid(false), perm(0) {}
+        __device__ State() : jvalid(false), dense(false), perm(0) {}
     };
     template <class W>
     static __device__ __forceinline__ void matrix_changed(const Team &, const ModeProg &, const W &, State &s)
@@ -248,6 +440,42 @@ struct LaneSolver {
         ni = sqrt(si) / (double)M.ni;
     }
 
+    // r = b + nonlinear rhs, reference accumulation order (row-indexed maps)
+    template <class TeamT, class W>
+    static __device__ __forceinline__ void assemble_rhs(const TeamT &tm, const ModeProg &M, const W &w, double *__restrict__ yp)
+    {
+        for (int row = tm.rank; row < NC; row += G) {
+            double acc = 0.0;
+            int c0 = __ldg(&M.b_all.ptr[row]), c1 = __ldg(&M.b_all.ptr[row + 1]);
+            for (int c = c0; c < c1; ++c) {
+                const unsigned wd = (unsigned)__ldg(&M.b_all.con[c]);
+                const double v = w.val[wd & ~CON_NEG];
+                acc += (wd & CON_NEG) ? -v : v;
+            }
+            c0 = __ldg(&M.r_nl.ptr[row]);
+            c1 = __ldg(&M.r_nl.ptr[row + 1]);
+            for (int c = c0; c < c1; ++c) {
+                const unsigned wd = (unsigned)__ldg(&M.r_nl.con[c]);
+                const double v = w.val[wd & ~CON_NEG];
+                acc += (wd & CON_NEG) ? -v : v;
+            }
+            yp[row * TS] = acc;
+        }
+    }
+
+    // SP: the zero-skipping factorisation met a zero / non-finite value: redo this solve with the dense arithmetic
+    template <class TeamT, class W>
+    static __device__ __noinline__ void dense_fallback(const TeamT &tm, const ModeProg &M, const W &w, State &s)
+    {
+        double *Jp = w.J.p, *yp = w.r.p, *xpp = w.xp.p;
+        assemble_rhs(tm, M, w, yp);
+        for (int e = 0; e < NC * NC; ++e) Jp[e * TS] = 0.0;
+        gather(tm, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
+        DenseDyn<NC>::factor(Jp, yp, s.perm);
+        DenseDyn<NC>::backward(Jp, yp, xpp, s.perm);
+        s.dense = true;
+    }
+
     template <class W>
     static __device__ __forceinline__ int newton(const Team &tm, const ModeProg &M, const W &w, State &s, Counters &cn,
                                                  int skip)
@@ -272,35 +500,42 @@ struct LaneSolver {
             const bool do_factor = !(linear && skip && s.jvalid);
             const bool do_solve = !(linear && skip && xp_ready);
             if (do_solve) {
-                for (int row = tm.rank; row < n; row += G) { // r = b + nonlinear rhs, reference accumulation order
-                    double acc = 0.0;
-                    int c0 = __ldg(&M.b_all.ptr[row]), c1 = __ldg(&M.b_all.ptr[row + 1]);
-                    for (int c = c0; c < c1; ++c) {
-                        const unsigned wd = (unsigned)__ldg(&M.b_all.con[c]);
-                        const double v = w.val[wd & ~CON_NEG];
-                        acc += (wd & CON_NEG) ? -v : v;
+                assemble_rhs(tm, M, w, yp);
+                if constexpr (SP) {
+                    int *__restrict__ mk = w.piv.p;
+                    bool ok = true;
+                    if (do_factor) {
+                        gather(tm, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
+                        ok = SparseLU<NC>::factor(Jp, yp, mk, w.aux, s.perm);
+                        s.dense = false;
+                        s.jvalid = linear;
+                        cn.c[CN_FACTOR]++;
+                    } else if (s.dense) {
+                        DenseDyn<NC>::forward(Jp, yp, s.perm);
+                    } else {
+                        SparseLU<NC>::forward(Jp, yp, mk, s.perm);
                     }
-                    c0 = __ldg(&M.r_nl.ptr[row]);
-                    c1 = __ldg(&M.r_nl.ptr[row + 1]);
-                    for (int c = c0; c < c1; ++c) {
-                        const unsigned wd = (unsigned)__ldg(&M.r_nl.con[c]);
-                        const double v = w.val[wd & ~CON_NEG];
-                        acc += (wd & CON_NEG) ? -v : v;
+                    if (ok) {
+                        if (s.dense)
+                            DenseDyn<NC>::backward(Jp, yp, xpp, s.perm);
+                        else
+                            ok = SparseLU<NC>::backward(Jp, yp, xpp, mk, s.perm);
                     }
-                    yp[row * TS] = acc;
-                }
-                if (do_factor) {
-                    for (int c = 0; c < n; ++c)
-                        for (int r = tm.rank; r < n; r += G) Jp[(c * NC + r) * TS] = 0.0;
-                    tm.sync();
-                    gather(tm, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
-                    factor(tm, Jp, yp, s.perm);
-                    s.jvalid = linear;
-                    cn.c[CN_FACTOR]++;
+                    if (!ok) dense_fallback(tm, M, w, s);
                 } else {
-                    forward(tm, Jp, yp, s.perm);
+                    if (do_factor) {
+                        for (int c = 0; c < n; ++c)
+                            for (int r = tm.rank; r < n; r += G) Jp[(c * NC + r) * TS] = 0.0;
+                        tm.sync();
+                        gather(tm, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
+                        factor(tm, Jp, yp, s.perm);
+                        s.jvalid = linear;
+                        cn.c[CN_FACTOR]++;
+                    } else {
+                        forward(tm, Jp, yp, s.perm);
+                    }
+                    backward(tm, Jp, yp, xpp, s.perm);
                 }
-                backward(tm, Jp, yp, xpp, s.perm);
                 xp_ready = true;
                 cn.c[CN_SOLVE]++;
             }
@@ -341,10 +576,10 @@ struct LaneSolver {
 
 // per-instance layout of the lane kernels, in doubles (each element is strided by 32/G inside the warp's region)
 struct LaneLayout {
-    int oJ, or_, ox, oxn, oxp, oval, ostate, oring, oprev, doubles;
+    int oJ, or_, ox, oxn, oxp, oval, ostate, oring, oprev, omk, doubles;
 };
 
-__host__ __device__ inline LaneLayout lane_layout(int nc, int n_slots, int n_dyn, int n_src, bool tran)
+__host__ __device__ inline LaneLayout lane_layout(int nc, int n_slots, int n_dyn, int n_src, bool tran, bool sparse = false)
 {
     LaneLayout t;
     int o = 0;
@@ -366,19 +601,41 @@ __host__ __device__ inline LaneLayout lane_layout(int nc, int n_slots, int n_dyn
     o += tran ? 2 * n_dyn : 0;
     t.oring = o;
     o += tran ? 3 * nc : 0;
+    t.omk = o; // structure words of the zero-skipping solver: 2 * nc ints
+    o += sparse ? nc : 0;
     t.doubles = o;
     return t;
 }
 
+// static structure words of J_full (rowmask(i) | colmask(i) << 16), one per index, computed once per block
+template <int NC>
+__device__ __forceinline__ void static_structure(const Gather &g, int *mk0)
+{
+    const int i = threadIdx.x & 31;
+    if (i < NC) {
+        unsigned rm = 0, cm = 0;
+        for (int d = 0; d < g.n_dst; ++d) {
+            const int off = __ldg(&g.dst[d]);
+            const int row = off & 0xffff, col = off >> 16;
+            if (row == i) rm |= 1u << col;
+            if (col == i) cm |= 1u << row;
+        }
+        mk0[i] = (int)(rm | (cm << 16));
+    }
+    __syncwarp();
+}
+
 // .tran for small circuits: starts from the start-up solution a.x_start left by a k_sync<.., AN_OP> launch
-template <int G, int NC, int AN>
+template <int G, int NC, int AN, bool SP = false>
 __global__ void __launch_bounds__(32) k_lanes(const __grid_constant__ RunArgs a)
 {
     static_assert(AN == AN_TRAN, "k_lanes is the .tran kernel; .op and .dc use k_sync");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int mk0[16];
     constexpr int TS = 32 / G;
     const DevProg &P = a.prog;
-    const LaneLayout T = lane_layout(NC, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN);
+    const LaneLayout T = lane_layout(NC, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN, SP);
+    if constexpr (SP) static_structure<NC>(P.tran.J_full, mk0);
     LaneTeam<G> tm;
     double *base = reinterpret_cast<double *>(smem_raw) + tm.slot;
     WsT<TS> w;
@@ -394,7 +651,9 @@ __global__ void __launch_bounds__(32) k_lanes(const __grid_constant__ RunArgs a)
     w.state.p = base + T.ostate * TS;
     w.ring.p = base + T.oring * TS;
     w.prev.p = AN == AN_TRAN ? base + T.oprev * TS : nullptr;
-    w.piv.p = nullptr;
+    // the structure words are ints interleaved like the doubles (word e of slot s at e * TS + s)
+    w.piv.p = SP ? reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + T.omk * TS) + tm.slot : nullptr;
+    w.aux = mk0;
     Counters cn;
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -403,7 +662,7 @@ __global__ void __launch_bounds__(32) k_lanes(const __grid_constant__ RunArgs a)
         first = __shfl_sync(0xffffffffu, first, 0);
         if (first >= a.batch) break;
         const long long inst = first + tm.slot;
-        if (inst < a.batch) run_instance<LaneTeam<G>, LaneSolver<G, NC>, AN>(tm, a, w, inst, cn);
+        if (inst < a.batch) run_instance<LaneTeam<G>, LaneSolver<G, NC, SP>, AN>(tm, a, w, inst, cn);
         __syncwarp();
     }
     // one atomic per counter per warp (counters are kept by rank 0 of each team)
@@ -475,20 +734,22 @@ struct SyncTeam { // same lanes as LaneTeam<G>, collectives on the whole (conver
 
 enum : int { PH_FETCH = 0, PH_SOLVE = 1, PH_IDLE = 2 };
 
-template <int G, int NC, int AN>
+template <int G, int NC, int AN, bool SP = false>
 __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
 {
     static_assert(AN == AN_OP || AN == AN_DC, "the warp-synchronous kernel covers .op and .dc");
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int mk0[16];
     constexpr int TS = 32 / G;
-    using Solver = LaneSolver<G, NC>;
-    using LSync = LaneSolver<G, NC>; // factor/forward/backward/resid are templated on the team object below
+    using Solver = LaneSolver<G, NC, SP>;
+    using LSync = LaneSolver<G, NC, SP>; // factor/forward/backward/resid are templated on the team object below
     const DevProg &P = a.prog;
     const ModeProg &M = AN == AN_OP ? P.op : P.dc;
     constexpr int n = NC; // == M.n (the host picks the instantiation)
     const bool linear = (M.n_nl == 0);
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const LaneLayout T = lane_layout(NC, P.n_slots, P.n_dyn, P.n_src, false);
+    const LaneLayout T = lane_layout(NC, P.n_slots, P.n_dyn, P.n_src, false, SP);
+    if constexpr (SP) static_structure<NC>(M.J_full, mk0);
     LaneTeam<G> tl;  // run-time mask: used only in the (divergent, rare) transition code
     SyncTeam<G> ts;  // constant full mask: used in the lock-step body
     double *base = reinterpret_cast<double *>(smem_raw) + tl.slot;
@@ -505,7 +766,12 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
     w.state.p = nullptr;
     w.ring.p = nullptr;
     w.prev.p = nullptr;
-    w.piv.p = nullptr;
+    w.piv.p = SP ? reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + T.omk * TS) + tl.slot : nullptr;
+    w.aux = mk0;
+    int *__restrict__ mk = w.piv.p;
+    if constexpr (SP) { // lanes that never get an instance still run the lock-step body: give them an empty structure
+        for (int i = 0; i < 2 * NC; ++i) mk[i * TS] = 0;
+    }
     double *__restrict__ Jp = w.J.p;
     double *__restrict__ yp = w.r.p;
     double *__restrict__ xpp = w.xp.p;
@@ -591,36 +857,43 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
         const bool any_solve = __any_sync(0xffffffffu, solving && do_solve);
         const bool any_factor = __any_sync(0xffffffffu, solving && do_factor);
         if (any_solve) {
-            for (int row = ts.rank; row < n; row += G) { // r = b + nonlinear rhs, reference accumulation order
-                double acc = 0.0;
-                int c0 = __ldg(&M.b_all.ptr[row]), c1 = __ldg(&M.b_all.ptr[row + 1]);
-                for (int c = c0; c < c1; ++c) {
-                    const unsigned wd = (unsigned)__ldg(&M.b_all.con[c]);
-                    const double v = w.val[wd & ~CON_NEG];
-                    acc += (wd & CON_NEG) ? -v : v;
+            LSync::assemble_rhs(ts, M, w, yp);
+            if constexpr (SP) {
+                bool ok = true;
+                if (any_factor) {
+                    // a team whose cached factors are still valid re-creates exactly the same factors: harmless
+                    gather(ts, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
+                    ok = SparseLU<NC>::factor(Jp, yp, mk, mk0, s.perm);
+                    s.dense = false;
+                    s.jvalid = linear;
+                    if (solving) cn.c[CN_FACTOR]++;
+                } else if (s.dense) {
+                    DenseDyn<NC>::forward(Jp, yp, s.perm);
+                } else {
+                    SparseLU<NC>::forward(Jp, yp, mk, s.perm);
                 }
-                c0 = __ldg(&M.r_nl.ptr[row]);
-                c1 = __ldg(&M.r_nl.ptr[row + 1]);
-                for (int c = c0; c < c1; ++c) {
-                    const unsigned wd = (unsigned)__ldg(&M.r_nl.con[c]);
-                    const double v = w.val[wd & ~CON_NEG];
-                    acc += (wd & CON_NEG) ? -v : v;
+                if (ok) {
+                    if (s.dense)
+                        DenseDyn<NC>::backward(Jp, yp, xpp, s.perm);
+                    else
+                        ok = SparseLU<NC>::backward(Jp, yp, xpp, mk, s.perm);
                 }
-                yp[row * TS] = acc;
-            }
-            if (any_factor) {
-                // a team whose cached factors are still valid re-creates exactly the same factors: harmless
-                for (int c = 0; c < n; ++c)
-                    for (int r = ts.rank; r < n; r += G) Jp[(c * NC + r) * TS] = 0.0;
-                ts.sync();
-                gather(ts, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
-                LSync::factor(ts, Jp, yp, s.perm);
-                s.jvalid = linear;
-                if (solving) cn.c[CN_FACTOR]++;
+                if (solving && !ok) LSync::dense_fallback(ts, M, w, s); // rare: zero / non-finite values
             } else {
-                LSync::forward(ts, Jp, yp, s.perm);
+                if (any_factor) {
+                    // a team whose cached factors are still valid re-creates exactly the same factors: harmless
+                    for (int c = 0; c < n; ++c)
+                        for (int r = ts.rank; r < n; r += G) Jp[(c * NC + r) * TS] = 0.0;
+                    ts.sync();
+                    gather(ts, M.J_full, w.J, decltype(w.J){nullptr}, w.val, NC);
+                    LSync::factor(ts, Jp, yp, s.perm);
+                    s.jvalid = linear;
+                    if (solving) cn.c[CN_FACTOR]++;
+                } else {
+                    LSync::forward(ts, Jp, yp, s.perm);
+                }
+                LSync::backward(ts, Jp, yp, xpp, s.perm);
             }
-            LSync::backward(ts, Jp, yp, xpp, s.perm);
             xp_ready = true;
             if (solving) cn.c[CN_SOLVE]++;
         }
@@ -707,11 +980,15 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
 }
 
 typedef void (*KernelFn)(const RunArgs);
-// defined in kern_lanes_*.cu; nullptr when (g, nc) is not instantiated
-KernelFn lanes_kernel_a(int g, int nc, int an);
-KernelFn lanes_kernel_b(int g, int nc, int an);
-KernelFn lanes_kernel_c(int g, int nc, int an);
-KernelFn lanes_kernel_d(int g, int nc, int an);
-KernelFn lanes_kernel_e(int g, int nc, int an);
+// defined in kern_lanes_*.cu (scripts/gen_lanes.py); nullptr when (g, nc, sp) is not instantiated there
+KernelFn lanes_kernel_a(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_b(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_c(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_d(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_e(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_s1(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_s2(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_s3(int g, int nc, int an, int sp);
+KernelFn lanes_kernel_s4(int g, int nc, int an, int sp);
 
 } // namespace ftsb

@@ -337,7 +337,7 @@ def test_thread_kernel_equals_generic_kernel_bitwise(name, an):
             t = circ.command("tran")
             r = be.run_tran(t.stop, t.step, capacity=700)
             outs.append((be.variant, r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final))
-    assert outs[0][0].startswith(("lanes", "sync")) and outs[1][0].startswith("warp"), (outs[0][0], outs[1][0])
+    assert outs[0][0].startswith(("lanes", "sync", "zskip")) and outs[1][0].startswith("warp"), (outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert np.array_equal(a, b, equal_nan=True)
 
@@ -402,3 +402,84 @@ def test_warp_kernel_equals_generic_kernel_bitwise(which):
     assert not ("r_n" in outs[1][0]), outs[1][0]
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# zero-skipping elimination (thread per instance, run-time structure masks) against the dense elimination
+# ------------------------------------------------------------------------------------------------------
+def _run_any(be, circ, an, cap=700):
+    if an == "op":
+        r = be.run_op()
+        return (r.status, r.n_iters, r.x)
+    if an == "dc":
+        d = circ.command("dc")
+        r = be.run_dc(d.source, d.start, d.stop, d.step)
+        return (r.status, r.points_done, r.n_iters, r.x)
+    t = circ.command("tran")
+    r = be.run_tran(t.stop, t.step, capacity=cap)
+    c = be.counters()
+    return (r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"], c["rej_newton"])
+
+
+ZSKIP_CASES = [(n, "op") for n in OP_NAMES] + [(n, "dc") for n in DC_NAMES] + [(n, "tran") for n in TRAN_NAMES]
+
+
+@pytest.mark.parametrize("name,an", ZSKIP_CASES)
+def test_zero_skipping_equals_dense_bitwise(name, an):
+    """Skipping `a - 0*p` updates must not change a single bit of any output (values compare equal, -0.0 == 0.0),
+    iteration count, record count or status, on every reference netlist (the three that fail by design included)."""
+    circ = load(name)
+    vals, fns = nl.monte_carlo(circ, 37)  # ragged: not a multiple of 32
+    outs, variants = [], []
+    for sparse in (1, 0):
+        be = BatchEngine(circ)
+        be.set_option("sparse", sparse)
+        be.set_params(vals, fns)
+        outs.append(_run_any(be, circ, an))
+        variants.append(be.variant)
+    assert variants[0].startswith("zskip") and not variants[1].startswith("zskip"), variants
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+SINGULAR = """* node 3 hangs on a capacitor only: in .op its row and column are zero (singular matrix)
+V1 1 0 1V
+R1 1 2 R=1k
+R2 2 0 R=1k
+C1 3 0 C=1p
+.OP
+.END
+"""
+
+
+def test_zero_skipping_singular_matrix_takes_the_dense_path(oracle_mod):
+    """A zero pivot column: the reference divides by zero and poisons everything with NaN (never converges).  The
+    zero-skipping solver must hand such a factorisation to the dense arithmetic and end with the same status."""
+    circ = nl.load(SINGULAR)
+    vals, fns = nl.monte_carlo(circ, 33)
+    st, it, x = oracle_mod.Oracle(circ).batch_op(vals, fns, threads=2)
+    for sparse in (1, 0):
+        be = BatchEngine(circ)
+        be.set_option("sparse", sparse)
+        be.set_params(vals, fns)
+        r = be.run_op()
+        assert (r.status == st).all(), (sparse, r.status[:4], st[:4])
+        assert (st != 0).all()
+
+
+@pytest.mark.parametrize("which", ["proj1_nl", "proj2", "nmos_test"])
+def test_zero_skipping_monte_carlo_vs_oracle(which, oracle_mod):
+    """Wide (+-40 %) Monte-Carlo spread so that instances sharing a warp take different pivot sequences."""
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else load(which)
+    B = 1000
+    vals, fns = nl.monte_carlo(circ, B, rel=0.4)
+    be = BatchEngine(circ)
+    be.set_option("sparse", 1)
+    be.set_params(vals, fns)
+    r = be.run_op()
+    assert be.variant.startswith("zskip")
+    st, it, x = oracle_mod.Oracle(circ).batch_op(vals, fns, threads=8)
+    assert (r.status == st).all()
+    ok = st == 0
+    assert (r.n_iters[ok] == it[ok]).all()
+    assert_close(r.x[ok], x[ok], f"{which} wide Monte-Carlo .op (zero-skipping)")
