@@ -12,6 +12,7 @@
 #include "../../include/ftsb.h"
 #include "compile.h"
 #include "solver_lanes.cuh"
+#include "solver_sparse.cuh"
 #include "solver_warp.cuh"
 
 using namespace ftsb;
@@ -58,6 +59,7 @@ struct ftsb_circuit {
     // staging of outputs when the caller's buffers are on the host
     DevBuf o_x, o_it, o_status, o_done, o_t, o_nrec, o_xf, i_start, i_stop, i_step;
     DevBuf s_x, s_it, s_st; // start-up solutions of .tran (small-circuit kernels)
+    DevBuf redo;            // instances the sparse kernels hand to the dense kernels
     std::string err;
     std::string variant = "none";
     long long launches = 0;
@@ -65,6 +67,8 @@ struct ftsb_circuit {
     int force_cta = 0;
     int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
     int lanes = 0;         // >0: lanes per instance requested for the dense small-circuit kernels (if built)
+    int sparse_warp = 1;   // 1 (default): structure-exploiting warp-per-instance kernels for n > 16
+    int fill_cap = 0;      // >0: run-time fill-in pool entries per instance of those kernels (0 = automatic)
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
                            // 2-3 warps per SM in shared memory and is latency bound)
@@ -120,6 +124,18 @@ ModeProg dev_mode(const int *base, const ModeOff &o)
     m.f_nl = dev_gather(base, o.f_nl);
     m.J_full = dev_gather(base, o.J_full);
     m.Ax = dev_gather(base, o.Ax);
+    m.sp.nnz = o.sp.nnz;
+    m.sp.n_pred = o.sp.n_pred;
+    m.sp.cptr = base + o.sp.cptr;
+    m.sp.erow = base + o.sp.erow;
+    m.sp.rptr = base + o.sp.rptr;
+    m.sp.rcol = base + o.sp.rcol;
+    m.sp.rent = base + o.sp.rent;
+    m.sp.n_long = o.sp.n_long;
+    m.sp.pad2 = 0;
+    m.sp.rlong = base + o.sp.rlong;
+    m.sp.lmap = base + o.sp.lmap;
+    m.sp.S = dev_gather(base, o.sp.S);
     return m;
 }
 
@@ -321,51 +337,150 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
     return 0;
 }
 
-static std::string po_variant_tag(const LaunchPlan &po) { return "op" + std::to_string(po.g); }
+// structure-exploiting warp-per-instance kernels (solver_sparse.cuh): n_start > 16.  Returns 0 when chosen.
+int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &fcap)
+{
+    if (!c->sparse_warp || c->force_generic || c->force_cta) return 1;
+    if (std::max(c->comp.n_start, 1) <= 16) return 1;
+    const ModeOff &mo = c->comp.mode[an]; // AN_OP / AN_DC / AN_TRAN index the modes
+    const int n = mo.n, nnz = mo.sp.nnz;
+    if (n < 1) return 1;
+    // run-time fill-in pool: partial pivoting may leave the predicted structure; an instance that exhausts the pool
+    // goes to the dense kernels.  Halve until one warp fits.
+    fcap = c->fill_cap > 0 ? c->fill_cap : std::max(64, nnz / 2);
+    fcap = (fcap + 1) & ~1;
+    if (n >= 0xfff0) return 1; // u16 indices
+    if (nnz + fcap >= 0xfff0) fcap = (0xfff0 - nnz - 2) & ~1;
+    if (fcap < 2) return 1;
+    KernelFn fn = sparse_kernel(an);
+    const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
+    SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    while (stat + ((T.bytes + 15) & ~(size_t)15) > c->smem_optin && fcap > 64 && c->fill_cap <= 0) {
+        fcap = (fcap / 2 + 1) & ~1;
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    }
+    const size_t per_warp = (T.bytes + 15) & ~(size_t)15;
+    int best_w = 0, best_occ = 0;
+    size_t best_smem = 0;
+    for (int wpb = 4; wpb >= 1; wpb >>= 1) {
+        const size_t smem = stat + per_warp * wpb;
+        if (smem > c->smem_optin) continue;
+        if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32 * wpb, smem) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        if (occ * wpb > best_occ * best_w) {
+            best_w = wpb;
+            best_occ = occ;
+            best_smem = smem;
+        }
+    }
+    if (!best_w) return 1;
+    if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    pl.fn = fn;
+    pl.g = 32;
+    pl.block = 32 * best_w;
+    pl.smem = best_smem;
+    pl.lay = c->comp.lay;
+    pl.scratch_bytes = 0;
+    pl.lanes = true; // .tran takes its start-up solution from a separate .op launch
+    const long long need = (batch + best_w - 1) / best_w;
+    pl.grid = (int)std::max(1LL, std::min(need, (long long)best_occ * c->sm_count));
+    c->variant = "spw_n" + std::to_string(n) + "/nnz" + std::to_string(nnz - mo.sp.n_pred) + "+" + std::to_string(mo.sp.n_pred) +
+                 "/fill" + std::to_string(fcap) + "/occ" + std::to_string(best_occ * best_w);
+    return 0;
+}
+
+int launch_kernel(ftsb_circuit *c, const LaunchPlan &pl, RunArgs &a)
+{
+    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+    void *args[] = {&a};
+    FTSB_CUDA(c, cudaLaunchKernel((const void *)pl.fn, dim3(pl.grid), dim3(pl.block), args, pl.smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
+// the dense / small-circuit kernels alone.  `dense_lanes`: the dense plan takes an external start-up solution.
+int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
+{
+    LaunchPlan ps, pd;
+    int fcap = 0;
+    const bool sparse = plan_sparse(c, an, a.batch, ps, fcap) == 0;
+    const std::string sv = c->variant;
+    int rc = plan_launch(c, an, a.batch, pd);
+    if (rc) return rc;
+    const std::string dv = c->variant;
+    if (pd.scratch_bytes) FTSB_CUDA(c, c->scratch.ensure(pd.scratch_bytes));
+    a.scratch = (double *)c->scratch.p;
+    if (sparse) {
+        FTSB_CUDA(c, c->redo.ensure((size_t)a.batch * 8));
+        RunArgs as = a;
+        as.prog.lay = ps.lay;
+        as.prog.op.sp.fcap = as.prog.dc.sp.fcap = as.prog.tran.sp.fcap = fcap;
+        as.redo_list = (long long *)c->redo.p;
+        as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
+        FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
+        rc = launch_kernel(c, ps, as);
+        if (rc) return rc;
+        a.in_list = as.redo_list;
+        a.in_count = as.redo_count;
+    }
+    a.prog.lay = pd.lay;
+    rc = launch_kernel(c, pd, a);
+    if (rc) return rc;
+    variant = sparse ? sv + "+redo:" + dv : dv;
+    return 0;
+}
 
 int launch(ftsb_circuit *c, int an, RunArgs &a)
 {
-    LaunchPlan pl;
-    int rc = plan_launch(c, an, a.batch, pl);
-    if (rc) return rc;
-    if (pl.scratch_bytes) FTSB_CUDA(c, c->scratch.ensure(pl.scratch_bytes));
     a.prog = c->prog;
-    a.prog.lay = pl.lay;
-    a.scratch = (double *)c->scratch.p;
     a.work = (unsigned long long *)c->work.p;
     a.counters = (unsigned long long *)c->counters.p;
     a.skip_refactor = c->skip_refactor;
-    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
     FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
-    if (pl.lanes && an == AN_TRAN) {
-        // start-up solutions (engine.rs:158-161) by the .op kernel, kept on the device for the .tran kernel
-        const std::string tran_variant = c->variant;
-        LaunchPlan po;
-        if (plan_small(c, AN_OP, a.batch, po) != 0) return fail(c, FTSB_E_UNSUPPORTED, "no start-up kernel for this circuit");
+    std::string v_op, v_main;
+    bool ext_start = false;
+    if (an == AN_TRAN) { // does the .tran kernel take its start-up solution (engine.rs:158-161) from an .op launch?
+        LaunchPlan t;
+        int fc = 0;
+        if (plan_sparse(c, an, a.batch, t, fc) == 0)
+            ext_start = true;
+        else {
+            int rc = plan_launch(c, an, a.batch, t);
+            if (rc) return rc;
+            ext_start = t.lanes;
+        }
+    }
+    if (ext_start) {
         const int ns = std::max(c->comp.n_start, 1);
         FTSB_CUDA(c, c->s_x.ensure((size_t)a.batch * ns * 8));
         FTSB_CUDA(c, c->s_it.ensure((size_t)a.batch * 4));
         FTSB_CUDA(c, c->s_st.ensure((size_t)a.batch * 4));
         RunArgs ao = a;
-        ao.prog.lay = po.lay;
         ao.x = (double *)c->s_x.p;
         ao.n_iters = (int *)c->s_it.p;
         ao.status = (int *)c->s_st.p;
-        void *oargs[] = {&ao};
-        FTSB_CUDA(c, cudaLaunchKernel((const void *)po.fn, dim3(po.grid), dim3(po.block), oargs, po.smem, c->stream));
-        c->launches++;
-        FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+        int rc = run_phase(c, AN_OP, ao, v_op);
+        if (rc) return rc;
         // the start-up solve is not an output row of .tran
         FTSB_CUDA(c, cudaMemsetAsync((unsigned long long *)c->counters.p + CN_POINTS, 0, 8, c->stream));
         a.x_start = (const double *)c->s_x.p;
         a.start_status = (const int *)c->s_st.p;
         a.n_start = ns;
-        c->variant = tran_variant + "+" + po_variant_tag(po);
     }
-    KernelFn fn = pl.fn;
-    void *args[] = {&a};
-    FTSB_CUDA(c, cudaLaunchKernel((const void *)fn, dim3(pl.grid), dim3(pl.block), args, pl.smem, c->stream));
-    c->launches++;
+    int rc = run_phase(c, an, a, v_main);
+    if (rc) return rc;
+    c->variant = ext_start ? v_main + "+op[" + v_op + "]" : v_main;
     return 0;
 }
 
@@ -489,7 +604,7 @@ void ftsb_destroy(ftsb_circuit *c)
     }
     DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
                       &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
-                      &c->s_st};
+                      &c->s_st, &c->redo};
     for (DevBuf *b : bufs) b->release();
     delete c;
 }
@@ -512,6 +627,10 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->lanes = (int)value;
     else if (!strcmp(name, "sparse"))
         c->sparse = value ? 1 : 0;
+    else if (!strcmp(name, "sparse_warp"))
+        c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "fill_cap"))
+        c->fill_cap = (int)value;
     else
         return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
     return 0;
@@ -758,6 +877,8 @@ int ftsb_get_counters(ftsb_circuit *c, ftsb_counters *out)
     out->lu_solve = (int64_t)h[CN_SOLVE];
     out->rej_newton = (int64_t)h[CN_REJ_NEWTON];
     out->rej_plte = (int64_t)h[CN_REJ_PLTE];
+    out->redo = (int64_t)h[CN_REDO];
+    out->reserved = (int64_t)h[CN_WHY];
     return 0;
 }
 
@@ -873,7 +994,7 @@ extern "C" int ftsb_lu_solve(int device, int32_t n, int64_t batch, const double 
         int block = ((n + 31) / 32) * 32;
         grid = (int)std::min<long long>(batch, (long long)prop.multiProcessorCount * 2);
         LU_CUDA(scr.ensure((size_t)grid * n * n * 8));
-        size_t smem = (96 + 2 * (size_t)n) * 8 + (size_t)n * 4 + 16;
+        size_t smem = (96 + 2 * (size_t)n) * 8 + (2 * (((size_t)n + 3) & ~(size_t)3) + 8) * 4 + 16; // piv + column list
         k_lu_cta<<<grid, block, smem>>>(n, batch, pa, pb, px, (double *)scr.p);
     }
     LU_CUDA(cudaGetLastError());

@@ -362,6 +362,118 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
             put_gather(im, g, o.J_full);
         }
         {
+            // Static structure for the sparse solver: J_full's pattern + predicted fill-in.
+            // The prediction eliminates the pattern with a guessed pivot per column: a candidate whose entry is a
+            // bare +-1 incidence constant (V-source / start-up inductor rows; conductances are normally < 1), else
+            // the row sitting at the diagonal position, else the candidate at the smallest position.  A wrong guess
+            // costs speed only: entries outside the static set become run-time fill-in.
+            const int n = m.n;
+            std::map<int, std::vector<const Con *>> by_dst; // key = row | col << 16: column-major order
+            for (const Con &c : m.a) by_dst[c.dst].push_back(&c);
+            std::vector<std::map<int, bool>> rows(std::max(n, 1)); // row -> {col -> is a bare unit constant}
+            for (auto &kv : by_dst) {
+                const int r = kv.first & 0xffff, cc = kv.first >> 16;
+                bool unit = kv.second.size() == 1 && (kv.second[0]->word & ~CON_NEG) == (unsigned)SLOT_ONE;
+                rows[r][cc] = unit;
+            }
+            std::vector<std::map<int, bool>> work = rows;
+            std::vector<int> pos(std::max(n, 1)), piv(std::max(n, 1));
+            for (int i = 0; i < n; ++i) pos[i] = piv[i] = i;
+            for (int k = 0; k < n; ++k) {
+                int P = -1, bestpos = 1 << 30;
+                bool bestunit = false;
+                for (int r = 0; r < n; ++r) {
+                    if (pos[r] < k) continue;
+                    auto it = work[r].find(k);
+                    if (it == work[r].end()) continue;
+                    const bool unit = it->second;
+                    const int rank = unit ? 0 : (pos[r] == k ? 1 : 2);
+                    const int brank = P < 0 ? 3 : (bestunit ? 0 : (bestpos == k ? 1 : 2));
+                    if (rank < brank || (rank == brank && pos[r] < bestpos)) {
+                        P = r;
+                        bestpos = pos[r];
+                        bestunit = unit;
+                    }
+                }
+                if (P < 0) continue; // structurally singular column: nothing to predict
+                const int rk = piv[k], pp = pos[P];
+                piv[k] = P;
+                piv[pp] = rk;
+                pos[P] = k;
+                pos[rk] = pp;
+                for (int r = 0; r < n; ++r) {
+                    if (pos[r] <= k || !work[r].count(k)) continue;
+                    for (auto &pc : work[P])
+                        if (pc.first > k) work[r][pc.first] = false; // updated (or filled) entries are not constants
+                }
+            }
+            // entries: column-major over the union pattern
+            std::vector<std::vector<int>> cols(std::max(n, 1)); // col -> rows ascending
+            int n_pred = 0;
+            for (int r = 0; r < n; ++r)
+                for (auto &pc : work[r]) {
+                    cols[pc.first].push_back(r);
+                    if (!rows[r].count(pc.first)) ++n_pred;
+                }
+            std::vector<int> cptr(n + 1, 0), erow, rptr(n + 1, 0), rcol, rent;
+            std::map<int, int> ent_of; // row | col << 16 -> e
+            for (int cc = 0; cc < n; ++cc) {
+                std::sort(cols[cc].begin(), cols[cc].end());
+                for (int r : cols[cc]) {
+                    ent_of[r | (cc << 16)] = (int)erow.size();
+                    erow.push_back(r);
+                }
+                cptr[cc + 1] = (int)erow.size();
+            }
+            for (int r = 0; r < n; ++r) {
+                for (auto &pc : work[r]) { // std::map: columns ascending
+                    rcol.push_back(pc.first);
+                    rent.push_back(ent_of[r | (pc.first << 16)]);
+                }
+                rptr[r + 1] = (int)rcol.size();
+            }
+            GatherBuild g;
+            g.ptr.push_back(0);
+            for (int e = 0; e < (int)erow.size(); ++e) {
+                g.dst.push_back(e);
+                // column of e: find by cptr
+                int cc = (int)(std::upper_bound(cptr.begin(), cptr.end(), e) - cptr.begin()) - 1;
+                auto it = by_dst.find(erow[e] | (cc << 16));
+                if (it != by_dst.end())
+                    for (int ph = 0; ph < 3; ++ph)
+                        for (const Con *c : it->second)
+                            if (c->phase == ph) g.con.push_back((int)c->word);
+                g.ptr.push_back((int)g.con.size());
+            }
+            o.sp.nnz = (int)erow.size();
+            o.sp.n_pred = n_pred;
+            o.sp.cptr = im.push(cptr);
+            o.sp.erow = im.push(erow);
+            o.sp.rptr = im.push(rptr);
+            o.sp.rcol = im.push(rcol);
+            o.sp.rent = im.push(rent);
+            {
+                // direct column -> entry maps for the longest rows (a supply rail touches every stage)
+                std::vector<std::pair<int, int>> bylen;
+                for (int r = 0; r < n; ++r)
+                    if (rptr[r + 1] - rptr[r] > SP_LONG_ROW) bylen.push_back({-(rptr[r + 1] - rptr[r]), r});
+                std::sort(bylen.begin(), bylen.end());
+                if ((int)bylen.size() > SP_MAX_LONG) bylen.resize(SP_MAX_LONG);
+                std::vector<int> rlong(std::max(n, 1), -1), lmap;
+                for (size_t li = 0; li < bylen.size(); ++li) {
+                    const int r = bylen[li].second;
+                    rlong[r] = (int)li;
+                    std::vector<int> mp(n, -1);
+                    for (int t = rptr[r]; t < rptr[r + 1]; ++t) mp[rcol[t]] = rent[t];
+                    lmap.insert(lmap.end(), mp.begin(), mp.end());
+                }
+                o.sp.n_long = (int)bylen.size();
+                o.sp.rlong = im.push(rlong);
+                o.sp.lmap = im.push(lmap);
+            }
+            put_gather(im, g, o.sp.S);
+        }
+        {
             // Ax, row-indexed flat list of (col, slot, sign) for the linear + companion part
             GatherBuild g;
             g.ptr.push_back(0);
@@ -432,7 +544,7 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
     L.oA = 0; // filled by the launcher (smem or global scratch)
     L.oJ = 0;
     L.opiv = 0;
-    L.ints = (ld + 3) & ~3;
+    L.ints = 2 * ((ld + 3) & ~3) + 8; // piv[ld] + the CTA solver's non-zero column list and its two counters
     L.mat_in_smem = 0;
     L.bytes = 0;
     out.ibuf = &im.ibuf;

@@ -19,10 +19,16 @@ struct GatherOff {
     int dst = 0, ptr = 0, con = 0, n_dst = 0, n_con = 0;
 };
 
+struct SparseOff {
+    int nnz = 0, n_pred = 0, cptr = 0, erow = 0, rptr = 0, rcol = 0, rent = 0, n_long = 0, rlong = 0, lmap = 0;
+    GatherOff S;
+};
+
 struct ModeOff {
     int n = 0, nv = 0, ni = 0, n_nl = 0, n_gfun = 0;
     int cls = 0, nl = 0;
     GatherOff A_lin, A_dyn, J_nl, b_all, r_nl, f_nl, J_full, Ax;
+    SparseOff sp;
 };
 
 struct Compiled {

@@ -22,7 +22,7 @@ namespace ftsb {
 // ---------------------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------------------
-enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_NEWTON = 4, CN_REJ_PLTE = 5, CN_COUNT = 8 };
+enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_NEWTON = 4, CN_REJ_PLTE = 5, CN_REDO = 6, CN_WHY = 7, CN_COUNT = 8 };
 
 struct RunArgs {
     DevProg prog;
@@ -57,7 +57,21 @@ struct RunArgs {
     const int *start_status; // [batch]
     int n_start;
     int pad3;
+    // sparse kernels: instances they abandon (zero / non-finite pivot, fill-in pool exhausted) ...
+    long long *redo_list;
+    unsigned long long *redo_count;
+    // ... and the dense kernels' list mode: run only the instances in_list[0 .. *in_count)
+    const long long *in_list;
+    const unsigned long long *in_count;
 };
+
+// next work item of a persistent kernel: an instance index, or -1 when the work is exhausted
+__device__ __forceinline__ long long next_instance(const RunArgs &a)
+{
+    const unsigned long long idx = atomicAdd(a.work, 1ULL);
+    if (a.in_list) return idx < *a.in_count ? a.in_list[idx] : -1;
+    return idx < (unsigned long long)a.batch ? (long long)idx : -1;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // teams
@@ -458,8 +472,23 @@ __device__ __forceinline__ void lu_factor(const Team &tm, int n, int ld, V J, IV
     const int r = tm.rank;
     const bool have = r < n;
     mypos = r;
+    // CTA teams (large n, matrix possibly in global memory): skip the updates `a - m*p` whose product is an exact
+    // zero.  Guarded so that the result is the dense one bit for bit: a row skips only if its multiplier is finite,
+    // and the pivot row's zero columns are skipped only if every entry of the pivot row is finite (0*inf = NaN must
+    // still poison).  clist / cnt live behind piv[] (Layout::ints).
+    int *clist = nullptr, *cnt = nullptr;
+    if constexpr (Team::kIsCta) {
+        clist = &piv[(n + 3) & ~3];
+        cnt = clist + ((n + 3) & ~3);
+    }
     for (int k = 0; k < n; ++k) {
         tm.sync();
+        if constexpr (Team::kIsCta) { // between two barriers: after step k-1's readers, before step k's writers
+            if (r == 0) {
+                cnt[0] = 0; // non-zero columns of the pivot row
+                cnt[1] = 0; // a non-finite entry in the pivot row
+            }
+        }
         double v = -1.0;
         int p = INT_MAX;
         if (have && mypos >= k) {
@@ -478,11 +507,35 @@ __device__ __forceinline__ void lu_factor(const Team &tm, int n, int ld, V J, IV
         }
         tm.sync();
         const int P = piv[k];
-        if (have && mypos > k) {
-            const double alpha = 1.0 / J[k * ld + P];
-            const double m = alpha * J[k * ld + r];
-            J[k * ld + r] = m;
-            for (int j = k + 1; j < n; ++j) J[j * ld + r] -= m * J[j * ld + P];
+        if constexpr (Team::kIsCta) {
+            for (int j = k + 1 + r; j < n; j += tm.size()) {
+                const double pv = J[j * ld + P];
+                if (pv != 0.0) clist[atomicAdd(&cnt[0], 1)] = j; // NaN != 0 too
+                if (!(fabs(pv) < __longlong_as_double(0x7ff0000000000000LL))) cnt[1] = 1;
+            }
+            tm.sync();
+            if (have && mypos > k) {
+                const double alpha = 1.0 / J[k * ld + P];
+                const double m = alpha * J[k * ld + r];
+                J[k * ld + r] = m;
+                const bool mfin = fabs(m) < __longlong_as_double(0x7ff0000000000000LL);
+                if (cnt[1] || !mfin) {
+                    for (int j = k + 1; j < n; ++j) J[j * ld + r] -= m * J[j * ld + P];
+                } else if (m != 0.0) {
+                    const int nc = cnt[0];
+                    for (int i = 0; i < nc; ++i) {
+                        const int j = clist[i];
+                        J[j * ld + r] -= m * J[j * ld + P];
+                    }
+                }
+            }
+        } else {
+            if (have && mypos > k) {
+                const double alpha = 1.0 / J[k * ld + P];
+                const double m = alpha * J[k * ld + r];
+                J[k * ld + r] = m;
+                for (int j = k + 1; j < n; ++j) J[j * ld + r] -= m * J[j * ld + P];
+            }
         }
     }
     tm.sync();
@@ -997,9 +1050,9 @@ __global__ void __launch_bounds__(128) k_subwarp(const __grid_constant__ RunArgs
     Counters cn;
     for (;;) {
         long long inst = 0;
-        if (tm.rank == 0) inst = (long long)atomicAdd(a.work, 1ULL);
+        if (tm.rank == 0) inst = next_instance(a);
         inst = tm.bcast_ll(inst);
-        if (inst >= a.batch) break;
+        if (inst < 0) break;
         run_instance<SubWarp<G>, SmemSolver<SubWarp<G>>, AN>(tm, a, w, inst, cn);
         tm.sync();
     }
@@ -1020,9 +1073,9 @@ __global__ void k_cta(const __grid_constant__ RunArgs a)
     Counters cn;
     for (;;) {
         long long inst = 0;
-        if (threadIdx.x == 0) inst = (long long)atomicAdd(a.work, 1ULL);
+        if (threadIdx.x == 0) inst = next_instance(a);
         inst = tm.bcast_ll(inst);
-        if (inst >= a.batch) break;
+        if (inst < 0) break;
         run_instance<CtaTeam, SmemSolver<CtaTeam>, AN>(tm, a, w, inst, cn);
         tm.sync();
     }

@@ -43,6 +43,29 @@ struct Gather {
     int n_con;
 };
 
+// Static structure of the Jacobian for the structure-exploiting (sparse) solver: the structurally non-zero
+// entries of J_full plus the fill-in a symbolic elimination predicts, in column-major order (entry index e:
+// column ascending, then row ascending).  Run-time fill-in outside this set is handled dynamically per instance.
+struct SparseProg {
+    int nnz;         // static entries
+    int n_pred;      // of which predicted fill-in (no stamp contributes: value 0.0 until an update touches it)
+    int fcap;        // run-time fill-in pool entries per instance (set by the launcher)
+    int pad;
+    const int *cptr; // [n + 1] entries of column c: e in [cptr[c], cptr[c + 1])
+    const int *erow; // [nnz]   row of entry e
+    const int *rptr; // [n + 1] row-ordered view: the t-th entry of row r, t in [rptr[r], rptr[r + 1]), columns ascending
+    const int *rcol; // [nnz]   its column
+    const int *rent; // [nnz]   its entry index e
+    int n_long;      // rows with many entries get a direct column -> entry map (at most SP_MAX_LONG of them)
+    int pad2;
+    const int *rlong; // [n]  index of the row's map, or -1
+    const int *lmap;  // [n_long][n] entry index of (row, col) or -1
+    Gather S;        // sv[e] = sum of the stamp contributions of entry e (dst[e] == e)
+};
+
+constexpr int SP_MAX_LONG = 4;
+constexpr int SP_LONG_ROW = 12; // a row is 'long' above this many static entries
+
 // one analysis mode: OP (start-up numbering, inductors are shorts with a current row), DC (inductors and
 // capacitors open), TRAN (trapezoidal companions)
 struct ModeProg {
@@ -62,6 +85,7 @@ struct ModeProg {
     // thread-per-instance kernels keep neither A nor b in memory:
     Gather J_full;  // J[dst] = linear + companion + nonlinear stamps, every structurally non-zero entry
     Gather Ax;      // row-indexed; con = slot | sign | col << AX_COL_SHIFT: (A x)[row] = sum of +-val[slot] * x[col]
+    SparseProg sp;  // structure-exploiting solver (solver_sparse.cuh)
 };
 constexpr int AX_COL_SHIFT = 20;
 constexpr unsigned AX_SLOT_MASK = (1u << AX_COL_SHIFT) - 1u;

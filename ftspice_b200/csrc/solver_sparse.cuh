@@ -1,0 +1,591 @@
+// solver_sparse.cuh — structure-exploiting elimination, one WARP per instance, any n (16 < n <= 4096).
+//
+// MNA matrices are very sparse (C4 ladder, n = 65: 192 structural non-zeros; C5 inverter chain, n = 258: 1 021 of
+// 66 564) and the reference's dense elimination (gauss_lu.rs:29-42) spends almost all of its n^3/3 updates on
+// `a - 0*p`.  Those leave `a` unchanged, so an elimination that touches only non-zero multipliers and non-zero
+// pivot-row entries — with the reference's pivot rule (first position with the strictly largest |a|), reciprocal
+// scaling, separate multiply / subtract and update order — returns the reference's numbers (up to the sign of a
+// zero) at a cost that grows with the number of non-zeros: C5 5.7 M element updates -> ~500.
+//
+// Storage per instance (shared memory): one f64 per entry of the *static* structure (J_full's pattern plus the
+// fill-in a symbolic elimination predicts at circuit-compile time, compile.cpp) and a pool of run-time fill-in
+// entries (partial pivoting is value dependent, so instances may deviate from the prediction) chained per row and
+// per column.  Rows never move: each carries its position.  The static structure itself (column lists, row
+// lists) is shared by the warps of a block.
+//
+// An instance whose elimination meets a zero / infinite / NaN pivot candidate, a non-finite solution component, or
+// runs out of fill-in pool, is abandoned (status ST_REDO) and put on a redo list: the dense kernels then run it
+// from scratch with the reference's full arithmetic (0*inf = NaN poisoning and all), so observable behaviour in
+// those cases is the reference's too.
+#pragma once
+#include "solver_warp.cuh"
+
+namespace ftsb {
+
+typedef unsigned short u16;
+constexpr u16 SP_NONE = 0xffff;
+constexpr int ST_REDO = 100; // internal: never returned to the caller
+
+struct SpLayout {
+    int osv, otval, oy, ox, oxn, oxp, oval, oprev, ostate, oring, doubles; // in doubles
+    int ofr, ofc, ofnr, ofnc, orh, och, opos, opiv, ope, otcol, halfs;      // in u16 after the doubles
+    int bmw, words;                                                          // fill bitmap: n rows x bmw u32, after the u16s
+    int fcap;
+    size_t bytes;
+};
+
+__host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_slots, int n_dyn, int n_src, bool tran)
+{
+    SpLayout t;
+    int o = 0;
+    auto take = [&](int c) {
+        int r = o;
+        o += (c + 1) & ~1;
+        return r;
+    };
+    t.fcap = fcap;
+    t.osv = take(nnz + fcap);
+    t.otval = take(n);
+    t.oy = take(n);
+    t.ox = take(n);
+    t.oxn = take(n);
+    t.oxp = take(n);
+    t.oval = take(n_slots);
+    t.oprev = take(tran ? 3 * n_src : 0);
+    t.ostate = take(tran ? 2 * n_dyn : 0);
+    t.oring = take(tran ? 3 * n : 0);
+    t.doubles = o;
+    int h = 0;
+    auto takeh = [&](int c) {
+        int r = h;
+        h += c;
+        return r;
+    };
+    t.ofr = takeh(fcap);
+    t.ofc = takeh(fcap);
+    t.ofnr = takeh(fcap);
+    t.ofnc = takeh(fcap);
+    t.orh = takeh(n);
+    t.och = takeh(n);
+    t.opos = takeh(n);
+    t.opiv = takeh(n);
+    t.ope = takeh(n);
+    t.otcol = takeh(n);
+    t.halfs = (h + 7) & ~7;
+    t.bmw = (n + 31) / 32;
+    t.words = (n * t.bmw + 3) & ~3;
+    t.bytes = (size_t)t.doubles * 8 + (size_t)t.halfs * 2 + (size_t)t.words * 4;
+    return t;
+}
+
+// u16 copy of the static structure, shared by the block:
+// cptr[n+1] rptr[n+1] rlong[n] erow[nnz] rcol[nnz] rent[nnz] lmap[n_long][n]
+__host__ __device__ inline size_t sp_static_bytes(int n, int nnz, int n_long)
+{
+    return (((size_t)2 * (n + 1) + n + 3 * (size_t)nnz + (size_t)n_long * n) * 2 + 15) & ~(size_t)15;
+}
+
+struct SpStatic {
+    const u16 *cptr, *rptr, *rlong, *erow, *rcol, *rent, *lmap;
+    int n, nnz;
+};
+
+struct SpInst {
+    double *sv, *tval;
+    u16 *fr, *fc, *fnr, *fnc, *rhead, *chead, *pos, *piv, *pe, *tcol;
+    unsigned *fbm; // bit (r, j): row r holds a run-time fill-in entry in column j
+    int fcap, bmw;
+};
+
+struct SparseWarpSolver {
+    using Team = WarpTeam;
+    static constexpr bool kHasA = false;
+    static constexpr bool kHasB = false;
+    static constexpr bool kExternalStartup = true;
+    struct State {
+        bool jvalid;
+        __device__ State() : jvalid(false) {}
+    };
+    template <class W>
+    static __device__ __forceinline__ void matrix_changed(const Team &, const ModeProg &, const W &, State &s)
+    {
+        s.jvalid = false;
+    }
+
+    template <class W>
+    static __device__ __forceinline__ void views(const ModeProg &M, const W &w, SpStatic &st, SpInst &in)
+    {
+        const int n = M.n, nnz = M.sp.nnz, fcap = M.sp.fcap;
+        const u16 *sb = reinterpret_cast<const u16 *>(w.aux);
+        st.n = n;
+        st.nnz = nnz;
+        st.cptr = sb;
+        st.rptr = sb + (n + 1);
+        st.rlong = sb + 2 * (n + 1);
+        st.erow = st.rlong + n;
+        st.rcol = st.erow + nnz;
+        st.rent = st.rcol + nnz;
+        st.lmap = st.rent + nnz;
+        in.fcap = fcap;
+        in.sv = w.J.p;
+        in.tval = w.J.p + ((nnz + fcap + 1) & ~1);
+        u16 *hb = reinterpret_cast<u16 *>(w.piv.p);
+        in.fr = hb;
+        in.fc = in.fr + fcap;
+        in.fnr = in.fc + fcap;
+        in.fnc = in.fnr + fcap;
+        in.rhead = in.fnc + fcap;
+        in.chead = in.rhead + n;
+        in.pos = in.chead + n;
+        in.piv = in.pos + n;
+        in.pe = in.piv + n;
+        in.tcol = in.pe + n;
+        const int halfs = (4 * fcap + 6 * n + 7) & ~7;
+        in.fbm = reinterpret_cast<unsigned *>(hb + halfs);
+        in.bmw = (n + 31) / 32;
+    }
+
+    // entry index of (r, j) in the static row list or the row's fill chain; -1 when absent
+    static __device__ __forceinline__ int lookup(const SpStatic &st, const SpInst &in, int r, int j)
+    {
+        const u16 li = st.rlong[r];
+        if (li != SP_NONE) { // long row: direct map
+            const u16 e = st.lmap[(int)li * st.n + j];
+            if (e != SP_NONE) return (int)e;
+        } else {
+            int q0 = st.rptr[r], q1 = st.rptr[r + 1];
+            if (q1 - q0 > 8) { // columns ascending: bisect down to a short range
+                while (q1 - q0 > 4) {
+                    const int mid = (q0 + q1) >> 1;
+                    if ((int)st.rcol[mid] <= j)
+                        q0 = mid;
+                    else
+                        q1 = mid;
+                }
+            }
+            for (int t = q0; t < q1; ++t)
+                if ((int)st.rcol[t] == j) return (int)st.rent[t];
+        }
+        if (!((in.fbm[r * in.bmw + (j >> 5)] >> (j & 31)) & 1u)) return -1; // no fill-in entry there
+        for (u16 f = in.rhead[r]; f != SP_NONE; f = in.fnr[f])
+            if ((int)in.fc[f] == j) return st.nnz + (int)f;
+        return -1;
+    }
+
+    // (largest v, then smallest pos) over the warp; v >= 0 or -1 (no candidate): compare the bit patterns as integers
+    static __device__ __forceinline__ void warp_argmax(double &v, int &p, int &r, int &e)
+    {
+        const long long key = v < 0.0 ? -1LL : __double_as_longlong(v);
+        const unsigned hi = (unsigned)((unsigned long long)(key + 1) >> 32), lo = (unsigned)(unsigned long long)(key + 1);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const bool ch = hi == mh;
+        const unsigned ml = __reduce_max_sync(0xffffffffu, ch ? lo : 0u);
+        const bool cl = ch && lo == ml;
+        const unsigned mp = __reduce_min_sync(0xffffffffu, cl ? (unsigned)p : 0xffffffffu);
+        const unsigned who = __ballot_sync(0xffffffffu, cl && (unsigned)p == mp);
+        const int src = __ffs((int)who) - 1;
+        v = __shfl_sync(0xffffffffu, v, src);
+        p = __shfl_sync(0xffffffffu, p, src);
+        r = __shfl_sync(0xffffffffu, r, src);
+        e = __shfl_sync(0xffffffffu, e, src);
+    }
+
+    // gauss_lu.rs:3-42 on the sparse storage, rhs y carried along.  Returns false -> abandon the instance (ST_REDO).
+    // (0 = ok, 1 = zero / non-finite pivot candidate, 2 = fill-in pool exhausted)
+    static __device__ int factor(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y)
+    {
+        const int n = st.n, nnz = st.nnz, lane = tm.rank;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        for (int i = lane; i < n; i += 32) {
+            in.pos[i] = (u16)i;
+            in.piv[i] = (u16)i;
+            in.rhead[i] = SP_NONE;
+            in.chead[i] = SP_NONE;
+        }
+        for (int i = lane; i < n * in.bmw; i += 32) in.fbm[i] = 0u;
+        int nfill = 0;
+        __syncwarp();
+        for (int k = 0; k < n; ++k) {
+            const int c0 = st.cptr[k], c1 = st.cptr[k + 1];
+            // ---- pivot search over the entries of column k held by rows at positions >= k ----
+            double bv = -1.0;
+            int bp = 0x7fffffff, br = -1, be = -1;
+            bool bad = false;
+            for (int t = c0 + lane; t < c1; t += 32) {
+                const int r = st.erow[t], p = in.pos[r];
+                if (p >= k) {
+                    const double v = fabs(in.sv[t]);
+                    bad |= !(v < INF);
+                    if (v > bv || (v == bv && p < bp)) {
+                        bv = v;
+                        bp = p;
+                        br = r;
+                        be = t;
+                    }
+                }
+            }
+            {
+                int i = 0;
+                for (u16 f = in.chead[k]; f != SP_NONE; f = in.fnc[f], ++i) {
+                    if ((i & 31) == lane) {
+                        const int r = in.fr[f], p = in.pos[r];
+                        if (p >= k) {
+                            const double v = fabs(in.sv[nnz + f]);
+                            bad |= !(v < INF);
+                            if (v > bv || (v == bv && p < bp)) {
+                                bv = v;
+                                bp = p;
+                                br = r;
+                                be = nnz + (int)f;
+                            }
+                        }
+                    }
+                }
+            }
+            warp_argmax(bv, bp, br, be);
+            if (__any_sync(0xffffffffu, bad) || !(bv > 0.0)) return 1;
+            const int P = br, eP = be, ppos = bp;
+            // ---- row swap (:19-27): positions only ----
+            if (lane == 0) {
+                const u16 rk = in.piv[k];
+                in.piv[k] = (u16)P;
+                in.piv[ppos] = rk;
+                in.pos[P] = (u16)k;
+                in.pos[rk] = (u16)ppos;
+                in.pe[k] = (u16)eP;
+            }
+            const double alpha = 1.0 / in.sv[eP]; // (:31)
+            const double yk = y[P];
+            // ---- pivot row: entries with column > k -> (tcol, tval) ----
+            int np = 0;
+            {
+                const int q0 = st.rptr[P], q1 = st.rptr[P + 1];
+                for (int tb = q0; tb < q1; tb += 32) {
+                    const int t = tb + lane;
+                    const bool take = t < q1 && (int)st.rcol[t] > k;
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (take) {
+                        const int idx = np + __popc(bal & ((1u << lane) - 1u));
+                        in.tcol[idx] = st.rcol[t];
+                        in.tval[idx] = in.sv[st.rent[t]];
+                    }
+                    np += __popc(bal);
+                }
+                for (u16 f = in.rhead[P]; f != SP_NONE; f = in.fnr[f]) {
+                    if ((int)in.fc[f] > k) {
+                        if (lane == 0) {
+                            in.tcol[np] = in.fc[f];
+                            in.tval[np] = in.sv[nnz + f];
+                        }
+                        ++np;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- eliminate column k from the rows below (:29-42), one row at a time, lanes over the pivot row ----
+            const int nstat = c1 - c0;
+            u16 f = in.chead[k];
+            for (int i = 0;; ++i) {
+                int r, e;
+                if (i < nstat) {
+                    e = c0 + i;
+                    r = st.erow[e];
+                } else {
+                    if (f == SP_NONE) break;
+                    e = nnz + (int)f;
+                    r = in.fr[f];
+                    f = in.fnc[f];
+                }
+                if ((int)in.pos[r] <= k) continue; // the pivot row itself, or a finished row (entry of U)
+                const double a = in.sv[e];
+                const double m = alpha * a;
+                __syncwarp();
+                if (lane == 0) in.sv[e] = m;
+                if (a == 0.0) continue; // a - 0*p == a
+                if (lane == 0) y[r] = y[r] - m * yk; // (:40)
+                for (int jb = 0; jb < np; jb += 32) {
+                    const int ji = jb + lane;
+                    bool need = false;
+                    int j = 0;
+                    double t = 0.0;
+                    if (ji < np) {
+                        j = in.tcol[ji];
+                        t = m * in.tval[ji];
+                        const int e2 = lookup(st, in, r, j);
+                        if (e2 >= 0)
+                            in.sv[e2] = in.sv[e2] - t; // (:35-39)
+                        else
+                            need = true;
+                    }
+                    unsigned fb = __ballot_sync(0xffffffffu, need);
+                    if (fb) { // run-time fill-in: the dense entry was +0.0
+                        if (nfill + __popc(fb) > in.fcap) return 2;
+                        const int mine = nfill + __popc(fb & ((1u << lane) - 1u));
+                        if (need) {
+                            in.fr[mine] = (u16)r;
+                            in.fc[mine] = (u16)j;
+                            in.sv[nnz + mine] = 0.0 - t;
+                        }
+                        __syncwarp();
+                        if (lane == 0) { // chain insertions in order (they share the row chain)
+                            for (unsigned bb = fb; bb; bb &= bb - 1u) {
+                                const int fi = nfill + __popc(fb & ((1u << (__ffs((int)bb) - 1)) - 1u));
+                                const int cj = in.fc[fi];
+                                in.fnr[fi] = in.rhead[r];
+                                in.rhead[r] = (u16)fi;
+                                in.fnc[fi] = in.chead[cj];
+                                in.chead[cj] = (u16)fi;
+                                in.fbm[r * in.bmw + (cj >> 5)] |= 1u << (cj & 31);
+                            }
+                        }
+                        nfill += __popc(fb);
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        return 0;
+    }
+
+    // a new right-hand side through the stored multipliers
+    static __device__ void forward(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y)
+    {
+        const int n = st.n, nnz = st.nnz, lane = tm.rank;
+        for (int k = 0; k < n - 1; ++k) {
+            const double yk = y[in.piv[k]];
+            const int c0 = st.cptr[k], c1 = st.cptr[k + 1];
+            __syncwarp();
+            for (int t = c0 + lane; t < c1; t += 32) {
+                const int r = st.erow[t];
+                if ((int)in.pos[r] > k) {
+                    const double m = in.sv[t];
+                    if (m != 0.0) y[r] = y[r] - m * yk;
+                }
+            }
+            int i = 0;
+            for (u16 f = in.chead[k]; f != SP_NONE; f = in.fnc[f], ++i) {
+                if ((i & 31) == lane) {
+                    const int r = in.fr[f];
+                    if ((int)in.pos[r] > k) {
+                        const double m = in.sv[nnz + f];
+                        if (m != 0.0) y[r] = y[r] - m * yk;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // gauss_lu.rs:44-53; false when a solution component is not finite
+    static __device__ bool backward(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y,
+                                    double *__restrict__ xp)
+    {
+        const int n = st.n, nnz = st.nnz, lane = tm.rank;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        bool ok = true;
+        for (int i = n - 1; i >= 0; --i) {
+            const int ri = in.piv[i];
+            const double xi = y[ri] / in.sv[in.pe[i]];
+            ok = ok && (fabs(xi) < INF);
+            if (lane == 0) xp[i] = xi;
+            const int c0 = st.cptr[i], c1 = st.cptr[i + 1];
+            __syncwarp();
+            for (int t = c0 + lane; t < c1; t += 32) {
+                const int r = st.erow[t];
+                if ((int)in.pos[r] < i) y[r] = y[r] - xi * in.sv[t];
+            }
+            int q = 0;
+            for (u16 f = in.chead[i]; f != SP_NONE; f = in.fnc[f], ++q) {
+                if ((q & 31) == lane) {
+                    const int r = in.fr[f];
+                    if ((int)in.pos[r] < i) y[r] = y[r] - xi * in.sv[nnz + f];
+                }
+            }
+            __syncwarp();
+        }
+        return ok;
+    }
+
+    // damped Newton (newtons_method.rs:19-71); same structure as WarpSolver::newton
+    template <class W>
+    static __device__ __forceinline__ int newton(const Team &tm, const ModeProg &M, const W &w, State &s, Counters &cn,
+                                                 int skip)
+    {
+        const int n = M.n;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        const bool linear = (M.n_nl == 0);
+        SpStatic st;
+        SpInst in;
+        views(M, w, st, in);
+        double *__restrict__ y = w.r.p;
+        double *__restrict__ xp = w.xp.p;
+
+        int flags = eval_nl(tm, M, w.x, w.val);
+        if (flags >> 20) return -ST_NMOS_UNREACHABLE;
+        double sov = INF, soi = INF, eov = INF, eoi = INF;
+        double ev = INF, ei = INF, sv = INF, si = INF;
+        bool xp_ready = false;
+        int it = 0;
+        while (it < 100 && !(sv < 0.001 * sov + 1e-6 && si < 0.001 * soi + 1e-9 && ev < 0.001 * eov + 1e-6 &&
+                             ei < 0.001 * eoi + 1e-9)) {
+            const bool do_factor = !(linear && skip && s.jvalid);
+            const bool do_solve = !(linear && skip && xp_ready);
+            if (do_solve) {
+                for (int row = tm.rank; row < n; row += 32) { // r = b + nonlinear rhs, reference accumulation order
+                    double acc = 0.0;
+                    int c0 = __ldg(&M.b_all.ptr[row]), c1 = __ldg(&M.b_all.ptr[row + 1]);
+                    for (int c = c0; c < c1; ++c) {
+                        const unsigned wd = (unsigned)__ldg(&M.b_all.con[c]);
+                        const double v = w.val[wd & ~CON_NEG];
+                        acc += (wd & CON_NEG) ? -v : v;
+                    }
+                    c0 = __ldg(&M.r_nl.ptr[row]);
+                    c1 = __ldg(&M.r_nl.ptr[row + 1]);
+                    for (int c = c0; c < c1; ++c) {
+                        const unsigned wd = (unsigned)__ldg(&M.r_nl.con[c]);
+                        const double v = w.val[wd & ~CON_NEG];
+                        acc += (wd & CON_NEG) ? -v : v;
+                    }
+                    y[row] = acc;
+                }
+                if (do_factor) {
+                    // values of the static entries from the slot table (predicted fill-in: no contribution -> 0.0)
+                    const Gather &g = M.sp.S;
+                    for (int d = tm.rank; d < g.n_dst; d += 32) {
+                        double acc = 0.0;
+                        const int c0 = __ldg(&g.ptr[d]), c1 = __ldg(&g.ptr[d + 1]);
+                        for (int c = c0; c < c1; ++c) {
+                            const unsigned wd = (unsigned)__ldg(&g.con[c]);
+                            const double v = w.val[wd & ~CON_NEG];
+                            acc += (wd & CON_NEG) ? -v : v;
+                        }
+                        in.sv[d] = acc;
+                    }
+                    __syncwarp();
+                    s.jvalid = false;
+                    if (const int why = factor(tm, st, in, y)) {
+                        cn.c[CN_REJ_NEWTON] = 0x100000000ull | (unsigned)why; // diagnostic: picked up by the kernel
+                        return -ST_REDO;
+                    }
+                    s.jvalid = linear;
+                    cn.c[CN_FACTOR]++;
+                } else {
+                    __syncwarp();
+                    forward(tm, st, in, y);
+                }
+                if (!backward(tm, st, in, y, xp)) {
+                    cn.c[CN_REJ_NEWTON] = 0x100000000ull | 3u;
+                    return -ST_REDO;
+                }
+                xp_ready = true;
+                cn.c[CN_SOLVE]++;
+            }
+            double qv = 0.0, qi = 0.0;
+            for (int i = tm.rank; i < n; i += 32) { // damped step (newtons_method.rs:73-77)
+                const double xi = w.x[i];
+                const double d = xp[i] - xi;
+                const double t = (1.3 / 16.0) * copysign(1.0, d) * log1p(16.0 * fabs(d));
+                w.xn[i] = xi + t;
+                if (__ldg(&M.cls[i]))
+                    qi += t * t;
+                else
+                    qv += t * t;
+            }
+            tm.sum2(qv, qi);
+            sv = sqrt(qv) / (double)M.nv;
+            si = sqrt(qi) / (double)M.ni;
+            tm.sync();
+
+            flags = eval_nl(tm, M, w.xn, w.val);
+            if (flags >> 20) return -ST_NMOS_UNREACHABLE;
+            WarpSolver<1>::resid(tm, M, w, w.xn, flags & 0xfffff, ev, ei);
+            if (isinf(ev) || isinf(ei)) return -ST_DIVERGED;
+            for (int i = tm.rank; i < n; i += 32) w.x[i] = w.xn[i];
+            tm.sync();
+            ++it;
+            cn.c[CN_NEWTON]++;
+            eov = ev;
+            eoi = ei;
+            sov = sv;
+            soi = si;
+        }
+        return it < 100 ? it : -ST_NOT_CONVERGED;
+    }
+};
+
+// one warp per instance; the warps of a block share the u16 copy of the static structure
+template <int AN>
+__global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevProg &P = a.prog;
+    const ModeProg &M = AN == AN_OP ? P.op : AN == AN_DC ? P.dc : P.tran;
+    const int n = M.n, nnz = M.sp.nnz;
+    {
+        u16 *sb = reinterpret_cast<u16 *>(smem_raw);
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+            sb[i] = (u16)__ldg(&M.sp.cptr[i]);
+            sb[n + 1 + i] = (u16)__ldg(&M.sp.rptr[i]);
+        }
+        u16 *rl = sb + 2 * (n + 1);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) rl[i] = (u16)__ldg(&M.sp.rlong[i]); // -1 -> SP_NONE
+        u16 *e0 = rl + n;
+        for (int i = threadIdx.x; i < nnz; i += blockDim.x) {
+            e0[i] = (u16)__ldg(&M.sp.erow[i]);
+            e0[nnz + i] = (u16)__ldg(&M.sp.rcol[i]);
+            e0[2 * nnz + i] = (u16)__ldg(&M.sp.rent[i]);
+        }
+        u16 *lm = e0 + 3 * nnz;
+        for (int i = threadIdx.x; i < M.sp.n_long * n; i += blockDim.x) lm[i] = (u16)__ldg(&M.sp.lmap[i]);
+    }
+    __syncthreads();
+    const int fcap = M.sp.fcap;
+    const SpLayout T = sp_layout(n, nnz, fcap, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN);
+    unsigned char *wb = smem_raw + sp_static_bytes(n, nnz, M.sp.n_long) + (size_t)(threadIdx.x >> 5) * ((T.bytes + 15) & ~(size_t)15);
+    double *base = reinterpret_cast<double *>(wb);
+    Ws w;
+    w.ld = n; // stride of the history ring
+    w.A.p = nullptr;
+    w.b.p = nullptr;
+    w.J.p = base + T.osv;
+    w.r.p = base + T.oy;
+    w.x.p = base + T.ox;
+    w.xn.p = base + T.oxn;
+    w.xp.p = base + T.oxp;
+    w.val.p = base + T.oval;
+    w.prev.p = AN == AN_TRAN ? base + T.oprev : nullptr;
+    w.state.p = base + T.ostate;
+    w.ring.p = base + T.oring;
+    w.piv.p = reinterpret_cast<int *>(base + T.doubles);
+    w.aux = reinterpret_cast<const int *>(smem_raw);
+    WarpTeam tm;
+    Counters cn;
+    for (;;) {
+        long long inst = 0;
+        if (tm.rank == 0) inst = next_instance(a);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst < 0) break;
+        Counters ci;
+        run_instance<WarpTeam, SparseWarpSolver, AN>(tm, a, w, inst, ci);
+        tm.sync();
+        int st = 0;
+        if (tm.rank == 0) st = a.status[inst];
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st == ST_REDO) { // hand the instance to the dense kernels
+            if (tm.rank == 0) {
+                a.redo_list[atomicAdd(a.redo_count, 1ULL)] = inst;
+                // why (diagnostic): 1 pivot, 2 fill pool, 3 non-finite solution; 20 bits per reason
+                const int why = (int)(ci.c[CN_REJ_NEWTON] & 3ull);
+                atomicAdd(&a.counters[CN_WHY], 1ULL << (20 * (why > 0 ? why - 1 : 0)));
+            }
+        } else {
+            for (int i = 0; i < 6; ++i) cn.c[i] += ci.c[i];
+        }
+    }
+    flush_counters(tm, a, cn);
+}
+
+KernelFn sparse_kernel(int an); // kern_sparse.cu
+
+} // namespace ftsb

@@ -313,9 +313,9 @@ __global__ void __launch_bounds__(32) k_warp(const __grid_constant__ RunArgs a)
     Counters cn;
     for (;;) {
         long long inst = 0;
-        if (tm.rank == 0) inst = (long long)atomicAdd(a.work, 1ULL);
+        if (tm.rank == 0) inst = next_instance(a);
         inst = __shfl_sync(0xffffffffu, inst, 0);
-        if (inst >= a.batch) break;
+        if (inst < 0) break;
         run_instance<WarpTeam, WarpSolver<RPT>, AN>(tm, a, w, inst, cn);
         tm.sync();
     }

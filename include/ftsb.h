@@ -104,7 +104,8 @@ typedef struct ftsb_counters {
     int64_t lu_solve;       /* forward/back substitutions executed                                    */
     int64_t rej_newton;     /* .tran attempts rejected by Newton failure                              */
     int64_t rej_plte;       /* .tran attempts rejected by the PLTE test                               */
-    int64_t reserved[2];
+    int64_t redo;           /* instances the structure-exploiting kernel handed to the dense kernels     */
+    int64_t reserved;       /* diagnostic: why (20 bits each: pivot zero/non-finite, fill pool, solution)  */
 } ftsb_counters;
 
 /* ---- library ---- */

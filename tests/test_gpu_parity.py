@@ -372,36 +372,97 @@ def test_lane_counts_agree_bitwise(name, an, lanes):
         assert np.array_equal(a, b, equal_nan=True)
 
 
-@pytest.mark.parametrize("which", ["ladder24", "ladder64", "inverter40", "ladder30_op"])
-def test_warp_kernel_equals_generic_kernel_bitwise(which):
-    """Mid-size circuits (16 < n <= 96): the warp-per-instance kernels (1-3 rows per lane, start-up .op as its own
-    launch) against the generic team / CTA kernels: every bit must agree."""
-    if which == "inverter40":
-        circ = nl.load(nl.inverter_chain_netlist(40, stop="2n", step="50p"))
-    elif which == "ladder30_op":
-        circ = nl.load(nl.ladder_netlist(30, stop="30n", step="1n") .replace(".TRAN 30n 1n", ".OP"))
-    else:
-        circ = nl.load(nl.ladder_netlist(int(which[6:]), "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )", stop="40n", step="1n"))
+def _mid_circuit(which):
+    if which.startswith("inverter"):
+        return nl.load(nl.inverter_chain_netlist(int(which[8:]), stop="2n", step="50p"))
+    if which == "ladder30_op":
+        return nl.load(nl.ladder_netlist(30, stop="30n", step="1n") .replace(".TRAN 30n 1n", ".OP"))
+    return nl.load(nl.ladder_netlist(int(which[6:]), "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )", stop="40n", step="1n"))
+
+
+def _run_mid(circ, vals, fns, opts, cap=300):
+    be = BatchEngine(circ)
+    for k, v in opts.items():
+        be.set_option(k, v)
+    be.set_params(vals, fns)
+    if circ.command("tran"):
+        t = circ.command("tran")
+        r = be.run_tran(t.stop, t.step, capacity=cap)
+        c = be.counters()
+        return be.variant, c, (r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"],
+                               c["rej_newton"], c["newton_iters"])
+    r = be.run_op()
+    c = be.counters()
+    return be.variant, c, (r.status, r.n_iters, r.x, c["solve_points"], c["newton_iters"])
+
+
+@pytest.mark.parametrize("which", ["ladder24", "ladder64", "inverter40", "ladder30_op", "inverter130"])
+def test_mid_size_kernels_agree_bitwise(which):
+    """Circuits with n > 16: the structure-exploiting warp kernel (default), the dense warp-per-instance kernel
+    (1-3 rows per lane, n <= 96) and the generic team / CTA kernel execute the same solution-path arithmetic on the
+    non-zeros: every output must compare equal, and so must the work counters."""
+    circ = _mid_circuit(which)
     B = 5
     vals, fns = nl.monte_carlo(circ, B)
-    outs = []
-    for generic in (0, 1):
-        be = BatchEngine(circ)
-        be.set_option("force_generic", generic)
-        be.set_params(vals, fns)
-        if circ.command("tran"):
-            t = circ.command("tran")
-            r = be.run_tran(t.stop, t.step, capacity=300)
-            c = be.counters()
-            outs.append((be.variant, r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final, c["solve_points"], c["rej_plte"],
-                         c["rej_newton"]))
-        else:
-            r = be.run_op()
-            outs.append((be.variant, r.status, r.n_iters, r.x))
-    assert outs[0][0].startswith("warp") and "r_n" in outs[0][0], outs[0][0]
-    assert not ("r_n" in outs[1][0]), outs[1][0]
-    for a, b in zip(outs[0][1:], outs[1][1:]):
+    v_sp, c_sp, o_sp = _run_mid(circ, vals, fns, {})
+    v_w, _, o_w = _run_mid(circ, vals, fns, {"sparse_warp": 0})
+    v_g, _, o_g = _run_mid(circ, vals, fns, {"force_generic": 1})
+    assert v_sp.startswith("spw_n"), v_sp
+    assert c_sp["redo"] == 0, c_sp
+    n_start = circ.n_start
+    assert (v_w.startswith("warp") and "r_n" in v_w) == (n_start <= 96), v_w
+    assert not ("r_n" in v_g) and not v_g.startswith("spw"), v_g
+    for a, b, c in zip(o_sp, o_w, o_g):
         assert np.array_equal(a, b, equal_nan=True)
+        assert np.array_equal(a, c, equal_nan=True)
+
+
+@pytest.mark.parametrize("which", ["ladder24", "inverter40", "ladder30_op"])
+def test_sparse_kernel_fill_pool_overflow_goes_to_the_dense_kernels(which):
+    """A fill-in pool that is too small: the instance is abandoned by the sparse kernel and redone by the dense
+    kernels; the results must not change."""
+    circ = _mid_circuit(which)
+    vals, fns = nl.monte_carlo(circ, 7, rel=0.3)
+    v0, c0, o0 = _run_mid(circ, vals, fns, {"sparse_warp": 0})
+    v1, c1, o1 = _run_mid(circ, vals, fns, {"fill_cap": 2})
+    assert v1.startswith("spw_n") and "redo" in v1, v1
+    for a, b in zip(o0, o1):
+        assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_sparse_kernel_singular_matrix_goes_to_the_dense_kernels(oracle_mod):
+    """n > 16 with a node that hangs on a capacitor only (zero pivot column in .op): the reference poisons the solve
+    with NaN and never converges; the sparse kernel must hand the instance to the dense arithmetic."""
+    text = nl.ladder_netlist(24, stop="30n", step="1n").replace(".TRAN 30n 1n", "Cx float 0 C=1p\n.OP")
+    circ = nl.load(text)
+    vals, fns = nl.monte_carlo(circ, 6)
+    st, it, x = oracle_mod.Oracle(circ).batch_op(vals, fns, threads=2)
+    assert (st != 0).all()
+    v, c, o = _run_mid(circ, vals, fns, {})
+    assert v.startswith("spw_n") and c["redo"] == 6, (v, c)
+    assert (o[0] == st).all()
+
+
+@pytest.mark.parametrize("which,B", [("inverter40", 64), ("ladder64", 48), ("inverter258", 6)])
+def test_sparse_kernel_vs_oracle(which, B, oracle_mod):
+    """The structure-exploiting kernel against the CPU oracle (dense elimination): status, record counts, iteration
+    counts, time stamps equal; unknowns within 1e-9 / 1e-12."""
+    if which == "inverter258":
+        circ = nl.load(nl.inverter_chain_netlist(256, stop="0.4n", step="50p"))
+    else:
+        circ = _mid_circuit(which)
+    vals, fns = nl.monte_carlo(circ, B)
+    t = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    r = be.run_tran(t.stop, t.step, capacity=400)
+    assert be.variant.startswith("spw_n"), be.variant
+    st, nrec, it, tt, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals, fns, t.stop, t.step, 400, threads=8)
+    assert (r.status == st).all() and (r.n_rec == nrec).all()
+    for i in range(B):
+        k = min(int(nrec[i]), 400)
+        assert (r.t[i, :k] == tt[i, :k]).all() and (r.n_iters[i, :k] == it[i, :k]).all()
+        assert_close(r.x[i, :k], x[i, :k], f"{which} instance {i}")
 
 
 # ------------------------------------------------------------------------------------------------------
