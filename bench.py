@@ -415,9 +415,25 @@ def main():
         value = pts_all * args.steps / (dev_ms_total * 1e-3)
         e2e_v = pts_all * args.steps / (e2e_ms_total * 1e-3)
         fm = flop_model(circ, wl["kind"] if wl["kind"] == "op" else "run")
-        exec_flops = cnt["lu_factor"] * fm["factor"] + cnt["lu_solve"] * fm["solve"] + cnt["newton_iters"] * fm["rest"]
         ref_flops = cnt["newton_iters"] * (fm["factor"] + fm["solve"] + fm["rest"])
-        kern_ms = float(np.mean(ms_dev))  # one kernel launch per step; events bracket exactly that launch
+        sparse = be.variant.startswith("spw")
+        if sparse:  # structure-exploiting kernel: flops it actually executed (device counter) + the per-iteration rest
+            exec_flops = cnt["sparse_flops"] + cnt["newton_iters"] * fm["rest"]
+        else:
+            exec_flops = cnt["lu_factor"] * fm["factor"] + cnt["lu_solve"] * fm["solve"] + cnt["newton_iters"] * fm["rest"]
+        kern_ms = float(np.mean(ms_dev))  # events bracket the step's launches (one kernel for .op/.dc; start-up + run for .tran)
+        v0 = be.variant.split("/")[0]
+        kname = ("k_spw" if v0.startswith("spw") else "k_sync" if v0.startswith(("sync", "zskip")) else
+                 "k_lanes" if v0.startswith("lanes") else "k_warp" if "r_n" in v0 else
+                 "k_cta" if v0.startswith("cta") else "k_subwarp")
+        traffic = None  # dram bytes per launch of that kernel from the committed ncu capture (profiles/traffic.json)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj.get(args.workload, {})
+            if ent.get("variant_prefix") and be.variant.startswith(ent["variant_prefix"]) and args.scale == 1.0:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
         fp64_peak = float(L.ftsb_measure_fp64_tflops(local_rank))
         achieved = exec_flops / (kern_ms * 1e-3) / 1e12
         peaks = {}
@@ -442,14 +458,15 @@ def main():
                     "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                         "kernel": f"k_{'cta' if be.variant.startswith('cta') else 'subwarp'}<{wl['kind']}> ({be.variant})",
+                         "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                         "kernel": f"{kname}<{wl['kind']}> ({be.variant})",
                          "kernel_ms": kern_ms, "executed_flops_per_launch": exec_flops,
                          "reference_equivalent_flops_per_launch": ref_flops,
                          "peak_source": "DFMA micro-benchmark in this run (ftsb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
                                         "fp64 entry. The solution path runs without FMA contraction (parity), so DMUL+DADD pairs "
                                         "cap it at 0.5 of this FMA peak",
                          "newton_iters_per_launch": cnt["newton_iters"], "lu_factor_per_launch": cnt["lu_factor"],
+                         "lu_solve_per_launch": cnt["lu_solve"], "redo_instances": cnt.get("redo", 0),
                          "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_launch": alg_bytes,

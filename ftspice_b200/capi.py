@@ -38,7 +38,7 @@ class FtsbTranOpts(ct.Structure):
 class FtsbCounters(ct.Structure):
     _fields_ = [("solve_points", ct.c_int64), ("newton_iters", ct.c_int64), ("lu_factor", ct.c_int64),
                 ("lu_solve", ct.c_int64), ("rej_newton", ct.c_int64), ("rej_plte", ct.c_int64),
-                ("redo", ct.c_int64), ("reserved", ct.c_int64)]
+                ("redo", ct.c_int64), ("sparse_flops", ct.c_int64)]
 
 
 class FtsbError(RuntimeError):

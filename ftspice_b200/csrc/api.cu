@@ -126,6 +126,8 @@ ModeProg dev_mode(const int *base, const ModeOff &o)
     m.Ax = dev_gather(base, o.Ax);
     m.sp.nnz = o.sp.nnz;
     m.sp.n_pred = o.sp.n_pred;
+    m.sp.fcap = 0;
+    m.sp.hist_global = 0;
     m.sp.cptr = base + o.sp.cptr;
     m.sp.erow = base + o.sp.erow;
     m.sp.rptr = base + o.sp.rptr;
@@ -338,8 +340,9 @@ int plan_launch(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl)
 }
 
 // structure-exploiting warp-per-instance kernels (solver_sparse.cuh): n_start > 16.  Returns 0 when chosen.
-int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &fcap)
+int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &fcap, int &hist_global)
 {
+    hist_global = 0;
     if (!c->sparse_warp || c->force_generic || c->force_cta) return 1;
     if (std::max(c->comp.n_start, 1) <= 16) return 1;
     const ModeOff &mo = c->comp.mode[an]; // AN_OP / AN_DC / AN_TRAN index the modes
@@ -347,7 +350,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     if (n < 1) return 1;
     // run-time fill-in pool: partial pivoting may leave the predicted structure; an instance that exhausts the pool
     // goes to the dense kernels.  Halve until one warp fits.
-    fcap = c->fill_cap > 0 ? c->fill_cap : std::max(64, nnz / 2);
+    fcap = c->fill_cap > 0 ? c->fill_cap : std::max(32, nnz / 2);
     fcap = (fcap + 1) & ~1;
     if (n >= 0xfff0) return 1; // u16 indices
     if (nnz + fcap >= 0xfff0) fcap = (0xfff0 - nnz - 2) & ~1;
@@ -355,9 +358,13 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     KernelFn fn = sparse_kernel(an);
     const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
     SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    if (an == AN_TRAN && T.bytes > 32 * 1024) { // large circuit: per-step history to global scratch (more warps per SM)
+        hist_global = 1;
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, true, true);
+    }
     while (stat + ((T.bytes + 15) & ~(size_t)15) > c->smem_optin && fcap > 64 && c->fill_cap <= 0) {
         fcap = (fcap / 2 + 1) & ~1;
-        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global != 0);
     }
     const size_t per_warp = (T.bytes + 15) & ~(size_t)15;
     int best_w = 0, best_occ = 0;
@@ -390,12 +397,12 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     pl.block = 32 * best_w;
     pl.smem = best_smem;
     pl.lay = c->comp.lay;
-    pl.scratch_bytes = 0;
     pl.lanes = true; // .tran takes its start-up solution from a separate .op launch
     const long long need = (batch + best_w - 1) / best_w;
     pl.grid = (int)std::max(1LL, std::min(need, (long long)best_occ * c->sm_count));
+    pl.scratch_bytes = (size_t)pl.grid * best_w * T.hist_doubles * 8;
     c->variant = "spw_n" + std::to_string(n) + "/nnz" + std::to_string(nnz - mo.sp.n_pred) + "+" + std::to_string(mo.sp.n_pred) +
-                 "/fill" + std::to_string(fcap) + "/occ" + std::to_string(best_occ * best_w);
+                 "/fill" + std::to_string(fcap) + (hist_global ? "/hg" : "") + "/occ" + std::to_string(best_occ * best_w);
     return 0;
 }
 
@@ -413,19 +420,23 @@ int launch_kernel(ftsb_circuit *c, const LaunchPlan &pl, RunArgs &a)
 int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
 {
     LaunchPlan ps, pd;
-    int fcap = 0;
-    const bool sparse = plan_sparse(c, an, a.batch, ps, fcap) == 0;
+    int fcap = 0, hist_global = 0;
+    const bool sparse = plan_sparse(c, an, a.batch, ps, fcap, hist_global) == 0;
     const std::string sv = c->variant;
     int rc = plan_launch(c, an, a.batch, pd);
     if (rc) return rc;
     const std::string dv = c->variant;
-    if (pd.scratch_bytes) FTSB_CUDA(c, c->scratch.ensure(pd.scratch_bytes));
+    {
+        const size_t need = std::max(pd.scratch_bytes, sparse ? ps.scratch_bytes : (size_t)0);
+        if (need) FTSB_CUDA(c, c->scratch.ensure(need));
+    }
     a.scratch = (double *)c->scratch.p;
     if (sparse) {
         FTSB_CUDA(c, c->redo.ensure((size_t)a.batch * 8));
         RunArgs as = a;
         as.prog.lay = ps.lay;
         as.prog.op.sp.fcap = as.prog.dc.sp.fcap = as.prog.tran.sp.fcap = fcap;
+        as.prog.tran.sp.hist_global = hist_global;
         as.redo_list = (long long *)c->redo.p;
         as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
@@ -452,8 +463,8 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
     bool ext_start = false;
     if (an == AN_TRAN) { // does the .tran kernel take its start-up solution (engine.rs:158-161) from an .op launch?
         LaunchPlan t;
-        int fc = 0;
-        if (plan_sparse(c, an, a.batch, t, fc) == 0)
+        int fc = 0, hg = 0;
+        if (plan_sparse(c, an, a.batch, t, fc, hg) == 0)
             ext_start = true;
         else {
             int rc = plan_launch(c, an, a.batch, t);
@@ -878,7 +889,7 @@ int ftsb_get_counters(ftsb_circuit *c, ftsb_counters *out)
     out->rej_newton = (int64_t)h[CN_REJ_NEWTON];
     out->rej_plte = (int64_t)h[CN_REJ_PLTE];
     out->redo = (int64_t)h[CN_REDO];
-    out->reserved = (int64_t)h[CN_WHY];
+    out->sparse_flops = (int64_t)h[CN_FLOPS];
     return 0;
 }
 

@@ -22,7 +22,10 @@ namespace ftsb {
 // ---------------------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------------------
-enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_NEWTON = 4, CN_REJ_PLTE = 5, CN_REDO = 6, CN_WHY = 7, CN_COUNT = 8 };
+// CN_FLOPS: floating-point operations the structure-exploiting solver executed in factorisations and substitutions
+// (the dense kernels' flops follow from CN_FACTOR / CN_SOLVE and n)
+enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_NEWTON = 4, CN_REJ_PLTE = 5, CN_FLOPS = 6, CN_LOCAL = 7,
+             CN_REDO = 7, CN_WHY = 8, CN_COUNT = 12 };
 
 struct RunArgs {
     DevProg prog;
@@ -233,10 +236,10 @@ struct WsT {
 using Ws = WsT<1>;
 
 struct Counters {
-    unsigned long long c[6];
+    unsigned long long c[CN_LOCAL];
     __device__ Counters()
     {
-        for (int i = 0; i < 6; ++i) c[i] = 0;
+        for (int i = 0; i < CN_LOCAL; ++i) c[i] = 0;
     }
 };
 
@@ -714,7 +717,7 @@ template <class Team>
 __device__ void flush_counters(const Team &tm, const RunArgs &a, const Counters &cn)
 {
     if (tm.rank == 0) {
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < CN_LOCAL; ++i)
             if (cn.c[i]) atomicAdd(&a.counters[i], cn.c[i]);
     }
 }

@@ -50,7 +50,7 @@ struct SparseProg {
     int nnz;         // static entries
     int n_pred;      // of which predicted fill-in (no stamp contributes: value 0.0 until an update touches it)
     int fcap;        // run-time fill-in pool entries per instance (set by the launcher)
-    int pad;
+    int hist_global; // .tran: C/L state and the history ring live in global scratch (set by the launcher)
     const int *cptr; // [n + 1] entries of column c: e in [cptr[c], cptr[c + 1])
     const int *erow; // [nnz]   row of entry e
     const int *rptr; // [n + 1] row-ordered view: the t-th entry of row r, t in [rptr[r], rptr[r + 1]), columns ascending

@@ -27,14 +27,16 @@ constexpr u16 SP_NONE = 0xffff;
 constexpr int ST_REDO = 100; // internal: never returned to the caller
 
 struct SpLayout {
-    int osv, otval, oy, ox, oxn, oxp, oval, oprev, ostate, oring, doubles; // in doubles
+    int osv, oy, ox, oxn, oxp, obv, oval, oprev, ostate, oring, doubles; // in doubles
+    int hist_doubles; // > 0: state + ring live in global scratch (that many doubles per resident warp), not here
     int ofr, ofc, ofnr, ofnc, orh, och, opos, opiv, ope, otcol, halfs;      // in u16 after the doubles
-    int bmw, words;                                                          // fill bitmap: n rows x bmw u32, after the u16s
+    int words;                                                               // fill signature: one u32 per row, after the u16s
     int fcap;
     size_t bytes;
 };
 
-__host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_slots, int n_dyn, int n_src, bool tran)
+__host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_slots, int n_dyn, int n_src, bool tran,
+                                              bool hist_global = false)
 {
     SpLayout t;
     int o = 0;
@@ -45,15 +47,22 @@ __host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_sl
     };
     t.fcap = fcap;
     t.osv = take(nnz + fcap);
-    t.otval = take(n);
     t.oy = take(n);
     t.ox = take(n);
     t.oxn = take(n);
     t.oxp = take(n);
+    t.obv = take(n); // b of the current solve (the residual subtracts it every iteration)
     t.oval = take(n_slots);
     t.oprev = take(tran ? 3 * n_src : 0);
-    t.ostate = take(tran ? 2 * n_dyn : 0);
-    t.oring = take(tran ? 3 * n : 0);
+    t.hist_doubles = 0;
+    if (tran && hist_global) {
+        t.ostate = 0;
+        t.oring = (2 * n_dyn + 1) & ~1;
+        t.hist_doubles = t.oring + ((3 * n + 1) & ~1);
+    } else {
+        t.ostate = take(tran ? 2 * n_dyn : 0);
+        t.oring = take(tran ? 3 * n : 0);
+    }
     t.doubles = o;
     int h = 0;
     auto takeh = [&](int c) {
@@ -72,8 +81,7 @@ __host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_sl
     t.ope = takeh(n);
     t.otcol = takeh(n);
     t.halfs = (h + 7) & ~7;
-    t.bmw = (n + 31) / 32;
-    t.words = (n * t.bmw + 3) & ~3;
+    t.words = (n + 3) & ~3;
     t.bytes = (size_t)t.doubles * 8 + (size_t)t.halfs * 2 + (size_t)t.words * 4;
     return t;
 }
@@ -93,8 +101,8 @@ struct SpStatic {
 struct SpInst {
     double *sv, *tval;
     u16 *fr, *fc, *fnr, *fnc, *rhead, *chead, *pos, *piv, *pe, *tcol;
-    unsigned *fbm; // bit (r, j): row r holds a run-time fill-in entry in column j
-    int fcap, bmw;
+    unsigned *sig; // bit (j & 31) of sig[r]: row r may hold a run-time fill-in entry in a column congruent to j
+    int fcap;
 };
 
 struct SparseWarpSolver {
@@ -104,7 +112,8 @@ struct SparseWarpSolver {
     static constexpr bool kExternalStartup = true;
     struct State {
         bool jvalid;
-        __device__ State() : jvalid(false) {}
+        int nfill; // run-time fill-in entries of the current factorisation
+        __device__ State() : jvalid(false), nfill(0) {}
     };
     template <class W>
     static __device__ __forceinline__ void matrix_changed(const Team &, const ModeProg &, const W &, State &s)
@@ -128,7 +137,7 @@ struct SparseWarpSolver {
         st.lmap = st.rent + nnz;
         in.fcap = fcap;
         in.sv = w.J.p;
-        in.tval = w.J.p + ((nnz + fcap + 1) & ~1);
+        in.tval = w.xn.p; // scratch during a factorisation: x_new is dead then
         u16 *hb = reinterpret_cast<u16 *>(w.piv.p);
         in.fr = hb;
         in.fc = in.fr + fcap;
@@ -141,8 +150,7 @@ struct SparseWarpSolver {
         in.pe = in.piv + n;
         in.tcol = in.pe + n;
         const int halfs = (4 * fcap + 6 * n + 7) & ~7;
-        in.fbm = reinterpret_cast<unsigned *>(hb + halfs);
-        in.bmw = (n + 31) / 32;
+        in.sig = reinterpret_cast<unsigned *>(hb + halfs);
     }
 
     // entry index of (r, j) in the static row list or the row's fill chain; -1 when absent
@@ -166,7 +174,7 @@ struct SparseWarpSolver {
             for (int t = q0; t < q1; ++t)
                 if ((int)st.rcol[t] == j) return (int)st.rent[t];
         }
-        if (!((in.fbm[r * in.bmw + (j >> 5)] >> (j & 31)) & 1u)) return -1; // no fill-in entry there
+        if (!((in.sig[r] >> (j & 31)) & 1u)) return -1; // no fill-in entry there
         for (u16 f = in.rhead[r]; f != SP_NONE; f = in.fnr[f])
             if ((int)in.fc[f] == j) return st.nnz + (int)f;
         return -1;
@@ -192,7 +200,9 @@ struct SparseWarpSolver {
 
     // gauss_lu.rs:3-42 on the sparse storage, rhs y carried along.  Returns false -> abandon the instance (ST_REDO).
     // (0 = ok, 1 = zero / non-finite pivot candidate, 2 = fill-in pool exhausted)
-    static __device__ int factor(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y)
+    // flops: executed floating-point operations; nfill_out: fill-in entries created
+    static __device__ int factor(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y,
+                                 unsigned long long &flops, int &nfill_out)
     {
         const int n = st.n, nnz = st.nnz, lane = tm.rank;
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -202,7 +212,7 @@ struct SparseWarpSolver {
             in.rhead[i] = SP_NONE;
             in.chead[i] = SP_NONE;
         }
-        for (int i = lane; i < n * in.bmw; i += 32) in.fbm[i] = 0u;
+        for (int i = lane; i < n; i += 32) in.sig[i] = 0u;
         int nfill = 0;
         __syncwarp();
         for (int k = 0; k < n; ++k) {
@@ -303,6 +313,7 @@ struct SparseWarpSolver {
                 if (lane == 0) in.sv[e] = m;
                 if (a == 0.0) continue; // a - 0*p == a
                 if (lane == 0) y[r] = y[r] - m * yk; // (:40)
+                flops += 3 + 2 * np;
                 for (int jb = 0; jb < np; jb += 32) {
                     const int ji = jb + lane;
                     bool need = false;
@@ -335,7 +346,7 @@ struct SparseWarpSolver {
                                 in.rhead[r] = (u16)fi;
                                 in.fnc[fi] = in.chead[cj];
                                 in.chead[cj] = (u16)fi;
-                                in.fbm[r * in.bmw + (cj >> 5)] |= 1u << (cj & 31);
+                                in.sig[r] |= 1u << (cj & 31);
                             }
                         }
                         nfill += __popc(fb);
@@ -345,6 +356,8 @@ struct SparseWarpSolver {
             }
             __syncwarp();
         }
+        flops += n; // reciprocals
+        nfill_out = nfill;
         return 0;
     }
 
@@ -407,6 +420,48 @@ struct SparseWarpSolver {
         return ok;
     }
 
+    // f = A x + H g - b and its class norms (mna.rs:25-29, node_vec_norm.rs:12-33); b comes from the copy the
+    // right-hand-side assembly of this Newton call left in w.b
+    template <class W, class V>
+    static __device__ __forceinline__ void resid(const Team &tm, const ModeProg &M, const W &w, V x, int nbad, double &nv,
+                                                 double &ni)
+    {
+        const int n = M.n;
+        double sv = 0.0, si = 0.0;
+        for (int row = tm.rank; row < n; row += 32) {
+            double ax = 0.0;
+            {
+                const int c0 = __ldg(&M.Ax.ptr[row]), c1 = __ldg(&M.Ax.ptr[row + 1]);
+                for (int c = c0; c < c1; ++c) {
+                    const unsigned wd = (unsigned)__ldg(&M.Ax.con[c]);
+                    const double v = w.val[wd & AX_SLOT_MASK];
+                    const double xc = x[(wd & ~CON_NEG) >> AX_COL_SHIFT];
+                    ax = fma((wd & CON_NEG) ? -v : v, xc, ax); // decision-only sum: FMA allowed
+                }
+            }
+            double hg = 0.0;
+            if (M.n_gfun > 0) {
+                int own_bad = 0;
+                const int c0 = __ldg(&M.f_nl.ptr[row]), c1 = __ldg(&M.f_nl.ptr[row + 1]);
+                for (int c = c0; c < c1; ++c) {
+                    const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
+                    const double v = w.val[wd & ~CON_NEG];
+                    own_bad += isfinite(v) ? 0 : 1;
+                    hg += (wd & CON_NEG) ? -v : v;
+                }
+                if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
+            }
+            const double f = ax + hg - w.b[row];
+            if (__ldg(&M.cls[row]))
+                si += f * f;
+            else
+                sv += f * f;
+        }
+        tm.sum2(sv, si);
+        nv = sqrt(sv) / (double)M.nv;
+        ni = sqrt(si) / (double)M.ni;
+    }
+
     // damped Newton (newtons_method.rs:19-71); same structure as WarpSolver::newton
     template <class W>
     static __device__ __forceinline__ int newton(const Team &tm, const ModeProg &M, const W &w, State &s, Counters &cn,
@@ -440,6 +495,7 @@ struct SparseWarpSolver {
                         const double v = w.val[wd & ~CON_NEG];
                         acc += (wd & CON_NEG) ? -v : v;
                     }
+                    w.b[row] = acc; // b of this solve: sources do not change inside a Newton call
                     c0 = __ldg(&M.r_nl.ptr[row]);
                     c1 = __ldg(&M.r_nl.ptr[row + 1]);
                     for (int c = c0; c < c1; ++c) {
@@ -464,7 +520,7 @@ struct SparseWarpSolver {
                     }
                     __syncwarp();
                     s.jvalid = false;
-                    if (const int why = factor(tm, st, in, y)) {
+                    if (const int why = factor(tm, st, in, y, cn.c[CN_FLOPS], s.nfill)) {
                         cn.c[CN_REJ_NEWTON] = 0x100000000ull | (unsigned)why; // diagnostic: picked up by the kernel
                         return -ST_REDO;
                     }
@@ -473,6 +529,7 @@ struct SparseWarpSolver {
                 } else {
                     __syncwarp();
                     forward(tm, st, in, y);
+                    cn.c[CN_FLOPS] += (unsigned long long)(st.nnz + s.nfill); // upper bound: 2 per entry of L, L ~ half
                 }
                 if (!backward(tm, st, in, y, xp)) {
                     cn.c[CN_REJ_NEWTON] = 0x100000000ull | 3u;
@@ -480,6 +537,7 @@ struct SparseWarpSolver {
                 }
                 xp_ready = true;
                 cn.c[CN_SOLVE]++;
+                cn.c[CN_FLOPS] += (unsigned long long)(st.nnz + s.nfill + n); // back substitution: 2 per entry of U + n divisions
             }
             double qv = 0.0, qi = 0.0;
             for (int i = tm.rank; i < n; i += 32) { // damped step (newtons_method.rs:73-77)
@@ -499,7 +557,7 @@ struct SparseWarpSolver {
 
             flags = eval_nl(tm, M, w.xn, w.val);
             if (flags >> 20) return -ST_NMOS_UNREACHABLE;
-            WarpSolver<1>::resid(tm, M, w, w.xn, flags & 0xfffff, ev, ei);
+            resid(tm, M, w, w.xn, flags & 0xfffff, ev, ei);
             if (isinf(ev) || isinf(ei)) return -ST_DIVERGED;
             for (int i = tm.rank; i < n; i += 32) w.x[i] = w.xn[i];
             tm.sync();
@@ -541,22 +599,27 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     }
     __syncthreads();
     const int fcap = M.sp.fcap;
-    const SpLayout T = sp_layout(n, nnz, fcap, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN);
+    const SpLayout T = sp_layout(n, nnz, fcap, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN, M.sp.hist_global != 0);
     unsigned char *wb = smem_raw + sp_static_bytes(n, nnz, M.sp.n_long) + (size_t)(threadIdx.x >> 5) * ((T.bytes + 15) & ~(size_t)15);
     double *base = reinterpret_cast<double *>(wb);
     Ws w;
     w.ld = n; // stride of the history ring
     w.A.p = nullptr;
-    w.b.p = nullptr;
     w.J.p = base + T.osv;
     w.r.p = base + T.oy;
     w.x.p = base + T.ox;
     w.xn.p = base + T.oxn;
     w.xp.p = base + T.oxp;
+    w.b.p = base + T.obv;
     w.val.p = base + T.oval;
     w.prev.p = AN == AN_TRAN ? base + T.oprev : nullptr;
-    w.state.p = base + T.ostate;
-    w.ring.p = base + T.oring;
+    {
+        // per-step history (C/L state, last three accepted x): shared memory, or — large circuits — a global
+        // scratch row per resident warp (touched once per accepted step, coalesced)
+        double *hb = T.hist_doubles ? a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles : base;
+        w.state.p = hb + T.ostate;
+        w.ring.p = hb + T.oring;
+    }
     w.piv.p = reinterpret_cast<int *>(base + T.doubles);
     w.aux = reinterpret_cast<const int *>(smem_raw);
     WarpTeam tm;
@@ -580,7 +643,7 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
                 atomicAdd(&a.counters[CN_WHY], 1ULL << (20 * (why > 0 ? why - 1 : 0)));
             }
         } else {
-            for (int i = 0; i < 6; ++i) cn.c[i] += ci.c[i];
+            for (int i = 0; i < CN_LOCAL; ++i) cn.c[i] += ci.c[i];
         }
     }
     flush_counters(tm, a, cn);

@@ -164,7 +164,7 @@ class BatchEngine:
         c = capi.FtsbCounters()
         capi.check(capi.lib().ftsb_get_counters(self.h, ct.byref(c)), self.h)
         return {k: int(getattr(c, k)) for k in ("solve_points", "newton_iters", "lu_factor", "lu_solve", "rej_newton",
-                                                "rej_plte", "redo", "reserved")}
+                                                "rej_plte", "redo", "sparse_flops")}
 
     # ---- parameters ----
     def compact_fns(self, fns: np.ndarray) -> np.ndarray:

@@ -105,7 +105,7 @@ typedef struct ftsb_counters {
     int64_t rej_newton;     /* .tran attempts rejected by Newton failure                              */
     int64_t rej_plte;       /* .tran attempts rejected by the PLTE test                               */
     int64_t redo;           /* instances the structure-exploiting kernel handed to the dense kernels     */
-    int64_t reserved;       /* diagnostic: why (20 bits each: pivot zero/non-finite, fill pool, solution)  */
+    int64_t sparse_flops;   /* flops executed by the structure-exploiting solver (factor + substitutions) */
 } ftsb_counters;
 
 /* ---- library ---- */
