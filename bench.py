@@ -62,12 +62,14 @@ M310 3 1 0 0 t_model
 """
 
 
-def make_workload_c3(scale: float, world: int):
+def make_workload_c3(scale: float, world: int, points: int = 32):
+    """1M sweep points cut into chains of `points` points; each chain is one reference `.dc` run (cold start at the chain
+    head, warm starts inside, src/engine.rs:116-127).  Shorter chains = more parallel work for the same point count."""
     circ = nl.load(NMOS_TEST)
-    chains_total = max(world, int(8192 * scale))
-    return dict(kind="dc", circ=circ, batch=chains_total // world, points=128, sweep="V01", lo=0.0, hi=3.4,
+    chains_total = max(world, int((1 << 20) // points * scale))
+    return dict(kind="dc", circ=circ, batch=chains_total // world, points=points, sweep="V01", lo=0.0, hi=3.4,
                 chains_total=chains_total,
-                label=f"C3 nmos_test .dc V01 0..3.4 as {chains_total} chains x 128 points (1M sweep points at scale 1), "
+                label=f"C3 nmos_test .dc V01 0..3.4 as {chains_total} chains x {points} points (1M sweep points at scale 1), "
                       f"sharded over the GPUs")
 
 
@@ -206,6 +208,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="batch-size multiplier (1.0 = the named config)")
     ap.add_argument("--tran-stop", type=float, default=None, help="override .tran stop time (c4/c5 shortening)")
+    ap.add_argument("--dc-points", type=int, default=32, help="points per .dc chain of workload c3 (1M points in total)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -218,7 +221,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    wl = make_workload_c3(args.scale, world) if args.workload == "c3" else make_workload(args.workload, args.scale)
+    wl = make_workload_c3(args.scale, world, args.dc_points) if args.workload == "c3" else make_workload(args.workload, args.scale)
     if args.tran_stop and wl["kind"] == "tran":
         wl["stop"] = args.tran_stop
         wl["label"] += f" [stop overridden to {args.tran_stop:g}s]"
@@ -483,11 +486,13 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}},
         }
         if not args.no_cpu and world == 1:
-            sample = args.cpu_sample or {"op": 4096, "dc": 64, "tran": 2}[wl["kind"]]
+            # bounded sample: a few seconds of single-thread CPU work
+            sample = args.cpu_sample or {"op": min(wl["batch"], 131072), "dc": min(wl["batch"], (1 << 20) // wl.get("points", 1)),
+                                         "tran": min(wl["batch"], 8)}[wl["kind"]]
             wl_cpu = dict(wl)
             samp = f"{sample} instances of the same workload (same seed, instances 0..{sample - 1})"
             if wl["kind"] == "tran":
-                wl_cpu["stop"] = wl["stop"] / 50.0
+                wl_cpu["stop"] = wl["stop"] / 20.0
                 samp += f", .tran stop shortened to {wl_cpu['stop']:g}s"
             p, s = cpu_run(wl_cpu, sample, 1)
             out["cpu_baseline"] = {"value": p / s, "unit": unit, "cores": 1, "kind": "port", "sample": samp,

@@ -544,3 +544,58 @@ def test_zero_skipping_monte_carlo_vs_oracle(which, oracle_mod):
     ok = st == 0
     assert (r.n_iters[ok] == it[ok]).all()
     assert_close(r.x[ok], x[ok], f"{which} wide Monte-Carlo .op (zero-skipping)")
+
+
+# ------------------------------------------------------------------------------------------------------
+# full BASELINE.json sizes: size-independent properties + oracle spot checks
+# ------------------------------------------------------------------------------------------------------
+def test_full_size_c2_batch_is_composition_independent(oracle_mod):
+    """C2 at its named size (65 536 Monte-Carlo instances of proj1-nl, .op).  An instance's result must not depend
+    on which other instances share its warp / its batch: a random subset run on its own returns the same bits.  The
+    subset is also checked against the oracle, and every instance must converge in the 21..33 iteration band the
+    survey measured."""
+    circ = nl.load(nl.PROJ1_NL)
+    B = 65536
+    vals, fns = nl.monte_carlo(circ, B)
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    r = be.run_op()
+    assert (r.status == 0).all()
+    assert r.n_iters.min() >= 20 and r.n_iters.max() <= 34, (r.n_iters.min(), r.n_iters.max())
+    assert be.counters()["solve_points"] == B and be.counters()["newton_iters"] == int(r.n_iters.sum())
+    rng = np.random.default_rng(7)
+    sub = np.sort(rng.choice(B, 777, replace=False))
+    be2 = BatchEngine(circ)
+    be2.set_params(vals[sub], fns[sub])
+    r2 = be2.run_op()
+    assert np.array_equal(r2.x, r.x[sub]) and np.array_equal(r2.n_iters, r.n_iters[sub])
+    st, it, x = oracle_mod.Oracle(circ).batch_op(vals[sub], fns[sub], threads=8)
+    assert (st == 0).all() and (it == r.n_iters[sub]).all()
+    assert_close(r.x[sub], x, "C2 full-size subset vs oracle")
+
+
+def test_full_size_c3_chains_prefix_property(oracle_mod):
+    """C3 at its named size (1 M sweep points of nmos_test as 32 768 chains x 32 points).  A chain is a warm-started
+    sequence, so the first 16 points of every 32-point chain must equal, bit for bit, the 16-point chain with the same
+    head and step; all chains complete; a sample of chains is checked against the oracle."""
+    circ = load("nmos_test")
+    C, Lp = 32768, 32
+    width = 3.4 / C
+    start = np.arange(C) * width
+    step = np.full(C, width / Lp)
+    stop = start + width - 0.25 * step
+    vals = np.broadcast_to(circ.vals, (C, circ.n_elems)).copy()
+    se = circ.elem_index("V01")
+    be = BatchEngine(circ)
+    be.set_params(vals)
+    r = be.run_dc(se, start, stop, step, max_points=Lp)
+    assert (r.status == 0).all() and (r.points_done == Lp).all()
+    assert be.counters()["solve_points"] == C * Lp
+    half = be.run_dc(se, start, start + 16 * step - 0.25 * step, step, max_points=16)
+    assert (half.points_done == 16).all()
+    assert np.array_equal(half.x, r.x[:, :16]) and np.array_equal(half.n_iters, r.n_iters[:, :16])
+    # the swept source's branch row reproduces the sweep values exactly: column of V01's node
+    sub = np.arange(0, C, 997)
+    st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals[sub], None, se, start[sub], stop[sub], step[sub], Lp, threads=8)
+    assert (st == 0).all() and (done == Lp).all() and (it == r.n_iters[sub]).all()
+    assert_close(r.x[sub].reshape(-1, r.x.shape[-1]), x.reshape(-1, x.shape[-1]), "C3 full-size chains vs oracle")
