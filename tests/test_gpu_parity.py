@@ -599,3 +599,48 @@ def test_full_size_c3_chains_prefix_property(oracle_mod):
     st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals[sub], None, se, start[sub], stop[sub], step[sub], Lp, threads=8)
     assert (st == 0).all() and (done == Lp).all() and (it == r.n_iters[sub]).all()
     assert_close(r.x[sub].reshape(-1, r.x.shape[-1]), x.reshape(-1, x.shape[-1]), "C3 full-size chains vs oracle")
+
+
+def test_sparse_kernel_dc_sweep_and_record_stride(oracle_mod):
+    """The structure-exploiting kernel's .dc instantiation (warm-started chains on a 30-stage inverter chain, n = 32)
+    and the .tran recording policy (stride 3, capacity 20), against the oracle and the dense kernels."""
+    text = nl.inverter_chain_netlist(30, stop="1n", step="50p")
+    circ = nl.load(text)
+    B = 9
+    vals, fns = nl.monte_carlo(circ, B)
+    se = circ.elem_index("Vin")
+    start = np.linspace(0.0, 0.4, B)
+    step = np.full(B, 0.02)
+    stop = start + 12 * step - 0.25 * step
+    outs = []
+    for opts in ({}, {"sparse_warp": 0}):
+        be = BatchEngine(circ)
+        for k, v in opts.items():
+            be.set_option(k, v)
+        be.set_params(vals, fns)
+        r = be.run_dc(se, start, stop, step, max_points=12)
+        outs.append((be.variant, r.status, r.points_done, r.n_iters, r.x))
+    assert outs[0][0].startswith("spw_n") and not outs[1][0].startswith("spw_n"), (outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a, b, equal_nan=True)
+    st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, fns, se, start, stop, step, 12, threads=4)
+    assert (outs[0][1] == st).all() and (outs[0][2] == done).all()
+    for i in range(B):
+        k = int(done[i])
+        assert (outs[0][3][i, :k] == it[i, :k]).all()
+        assert_close(outs[0][4][i, :k], x[i, :k], f"inverter30 .dc chain {i}")
+    # .tran with a recording stride
+    t = circ.command("tran")
+    full = BatchEngine(circ)
+    full.set_params(vals, fns)
+    rf = full.run_tran(t.stop, t.step, capacity=200)
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    rs = be.run_tran(t.stop, t.step, capacity=20, rec_stride=3)
+    assert be.variant.startswith("spw_n")
+    assert (rs.n_rec == rf.n_rec).all() and (rs.status == rf.status).all()
+    for i in range(B):
+        kept = min(20, (int(rf.n_rec[i]) + 2) // 3)
+        assert np.array_equal(rs.t[i, :kept], rf.t[i, 0:3 * kept:3])
+        assert np.array_equal(rs.x[i, :kept], rf.x[i, 0:3 * kept:3])
+    assert np.array_equal(rs.x_final, rf.x_final)
