@@ -6,12 +6,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/ftsb.h"
 #include "compile.h"
 #include "solver_lanes.cuh"
+#include "solver_plan.cuh"
 #include "solver_sparse.cuh"
 #include "solver_warp.cuh"
 
@@ -60,6 +62,12 @@ struct ftsb_circuit {
     DevBuf o_x, o_it, o_status, o_done, o_t, o_nrec, o_xf, i_start, i_stop, i_step;
     DevBuf s_x, s_it, s_st; // start-up solutions of .tran (small-circuit kernels)
     DevBuf redo;            // instances the sparse kernels hand to the dense kernels
+    // learned elimination plans (plan.h) per analysis mode (.op, .dc): built by a pilot run on the first call
+    PlanHost plan_host[2];
+    DevBuf plan_buf[2], trace;
+    int plan_state[2] = {0, 0}; // 0 = not tried, 1 = plans available, -1 = no usable plan
+    int plan_opt = 1;           // 1: use the plan-interpreting kernels for n <= 16 (.op / .dc)
+    int plan_lanes = 0;         // lanes per instance of those kernels (0 = automatic)
     std::string err;
     std::string variant = "none";
     long long launches = 0;
@@ -415,13 +423,112 @@ int launch_kernel(ftsb_circuit *c, const LaunchPlan &pl, RunArgs &a)
     return 0;
 }
 
+// ---- learned elimination plans for small circuits (plan.h, solver_plan.cuh) ---------------------------------
+// First .op / .dc call of a handle: a pilot run of the dense kernel over the first PLAN_PILOT instances records the
+// pivot sequence of every factorisation; the host turns the most frequent sequences into plans.
+int learn_plans(ftsb_circuit *c, int an, const RunArgs &a)
+{
+    c->plan_state[an] = -1;
+    LaunchPlan pd;
+    if (plan_lanes(c, an, std::min<long long>(a.batch, PLAN_PILOT), pd) != 0) return 0;
+    const long long sample = std::min<long long>(a.batch, PLAN_PILOT);
+    const size_t tb = (size_t)sample * PLAN_TRACE_MAX * 8;
+    FTSB_CUDA(c, c->trace.ensure(tb));
+    FTSB_CUDA(c, cudaMemsetAsync(c->trace.p, 0, tb, c->stream));
+    RunArgs ap = a;
+    ap.batch = sample;
+    ap.prog.lay = pd.lay;
+    ap.trace = (unsigned long long *)c->trace.p;
+    ap.in_list = nullptr;
+    ap.in_count = nullptr;
+    int rc = launch_kernel(c, pd, ap);
+    if (rc) return rc;
+    std::vector<unsigned long long> tr((size_t)sample * PLAN_TRACE_MAX);
+    FTSB_CUDA(c, cudaMemcpyAsync(tr.data(), c->trace.p, tb, cudaMemcpyDeviceToHost, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    // the pilot's counters must not leak into the caller's run
+    FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
+    std::map<unsigned long long, long long> hist;
+    for (unsigned long long v : tr)
+        if (v) ++hist[v];
+    const ModeOff &mo = c->comp.mode[an];
+    const std::vector<int> &ib = c->comp.ints();
+    std::vector<int> jdst(ib.begin() + mo.J_full.dst, ib.begin() + mo.J_full.dst + mo.J_full.n_dst);
+    std::vector<std::pair<uint64_t, long long>> perms(hist.begin(), hist.end());
+    PlanHost &ph = c->plan_host[an];
+    if (!build_plans(mo.n, jdst, perms, ph)) return 0;
+    FTSB_CUDA(c, c->plan_buf[an].ensure(ph.ibuf.size() * 4));
+    FTSB_CUDA(c, cudaMemcpyAsync(c->plan_buf[an].p, ph.ibuf.data(), ph.ibuf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream)); // ph.ibuf is pageable
+    c->plan_state[an] = 1;
+    return 0;
+}
+
+// Returns 0 when the plan kernel was chosen.
+int plan_plans(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, PlanProg &pp)
+{
+    if (an != AN_OP && an != AN_DC) return 1;
+    if (!c->plan_opt || c->force_generic || c->force_cta || c->sparse || c->lanes > 0) return 1;
+    if (c->plan_state[an] != 1) return 1;
+    const PlanHost &ph = c->plan_host[an];
+    const ModeOff &mo = c->comp.mode[an];
+    const int *base = (const int *)c->plan_buf[an].p;
+    pp.K = ph.K;
+    pp.S = ph.S;
+    pp.nnz0 = ph.nnz0;
+    pp.n = ph.n;
+    pp.rec = reinterpret_cast<const int4 *>(base + ph.off_rec);
+    pp.cand = base + ph.off_cand;
+    pp.mult = base + ph.off_mult;
+    pp.upd = base + ph.off_upd;
+    pp.bu = base + ph.off_bu;
+    pp.next = reinterpret_cast<const signed char *>(base + ph.off_next);
+    pp.jdst = base + ph.off_jdst;
+    const int g = c->plan_lanes == 1 || c->plan_lanes == 2 || c->plan_lanes == 4 ? c->plan_lanes : (mo.n <= 4 ? 1 : mo.n <= 8 ? 2 : 4);
+    KernelFn fn = plan_kernel(g, an);
+    const PlanLayout T = plan_layout(mo.n, ph.S, c->comp.n_slots, mo.n_nl == 0);
+    const size_t smem = (size_t)T.doubles * (32 / g) * 8;
+    if (smem > c->smem_optin) return 1;
+    if (cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return 1;
+    }
+    pl.fn = fn;
+    pl.g = g;
+    pl.block = 32;
+    pl.smem = smem;
+    pl.lay = c->comp.lay;
+    pl.scratch_bytes = 0;
+    pl.lanes = true;
+    const int per_warp = 32 / g;
+    pl.grid = (int)std::max(1LL, std::min((batch + per_warp - 1) / per_warp, (long long)occ * c->sm_count));
+    c->variant = "plan" + std::to_string(ph.K) + "g" + std::to_string(g) + "n" + std::to_string(mo.n) + "/S" + std::to_string(ph.S) +
+                 "/occ" + std::to_string(occ);
+    return 0;
+}
+
 // one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
 // the dense / small-circuit kernels alone.  `dense_lanes`: the dense plan takes an external start-up solution.
 int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
 {
     LaunchPlan ps, pd;
     int fcap = 0, hist_global = 0;
-    const bool sparse = plan_sparse(c, an, a.batch, ps, fcap, hist_global) == 0;
+    bool sparse = plan_sparse(c, an, a.batch, ps, fcap, hist_global) == 0;
+    bool planned = false;
+    if (!sparse && (an == AN_OP || an == AN_DC) && std::max(c->comp.n_start, 1) <= 16 && c->plan_opt && !c->force_generic &&
+        !c->force_cta && !c->sparse && c->lanes <= 0 && a.batch >= 64) {
+        if (c->plan_state[an] == 0) {
+            int rcl = learn_plans(c, an, a);
+            if (rcl) return rcl;
+        }
+        planned = plan_plans(c, an, a.batch, ps, a.plan) == 0;
+        sparse = planned; // same launch protocol: first kernel + redo list + dense pass
+    }
     const std::string sv = c->variant;
     int rc = plan_launch(c, an, a.batch, pd);
     if (rc) return rc;
@@ -615,7 +722,7 @@ void ftsb_destroy(ftsb_circuit *c)
     }
     DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
                       &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
-                      &c->s_st, &c->redo};
+                      &c->s_st, &c->redo, &c->plan_buf[0], &c->plan_buf[1], &c->trace};
     for (DevBuf *b : bufs) b->release();
     delete c;
 }
@@ -638,6 +745,10 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->lanes = (int)value;
     else if (!strcmp(name, "sparse"))
         c->sparse = value ? 1 : 0;
+    else if (!strcmp(name, "plan"))
+        c->plan_opt = value ? 1 : 0;
+    else if (!strcmp(name, "plan_lanes"))
+        c->plan_lanes = (int)value;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))

@@ -15,6 +15,7 @@
 
 #include <climits>
 
+#include "plan.h"
 #include "prog.h"
 
 namespace ftsb {
@@ -66,6 +67,9 @@ struct RunArgs {
     // ... and the dense kernels' list mode: run only the instances in_list[0 .. *in_count)
     const long long *in_list;
     const unsigned long long *in_count;
+    // learned elimination plans (solver_plan.cuh) and, in the pilot run that learns them, the pivot-sequence trace
+    PlanProg plan;
+    unsigned long long *trace; // [batch][PLAN_TRACE_MAX] nibble-packed position -> row of every factorisation (ring)
 };
 
 // next work item of a persistent kernel: an instance index, or -1 when the work is exhausted

@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
     long long k = 0, count = 0;
     double dc_start = 0.0, dc_step = 0.0;
     const int sweep_slot = AN == AN_DC ? __ldg(&P.src[5 * a.sweep_src + 1]) : 0;
+    int tcnt = 0; // factorisations of the current instance recorded in the pivot trace (pilot runs only)
 
     for (;;) {
         // ---------------- transitions ----------------
@@ -800,7 +801,11 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
                 first = __shfl_sync(0xffffffffu, first, 0);
                 // my team's index among the needy ones (slot bits live in lanes 0..kSlots-1)
                 const unsigned below = need & ((1u << tl.slot) - 1u);
-                if (phase == PH_FETCH) inst = first + __popc(below);
+                if (phase == PH_FETCH) {
+                    inst = first + __popc(below);
+                    if (a.in_list) inst = (unsigned long long)inst < *a.in_count ? a.in_list[inst] : a.batch; // list mode
+                    tcnt = 0;
+                }
             }
         }
         if (phase == PH_FETCH) {
@@ -889,6 +894,8 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
                     LSync::factor(ts, Jp, yp, s.perm);
                     s.jvalid = linear;
                     if (solving) cn.c[CN_FACTOR]++;
+                    if (a.trace && solving && do_factor && ts.rank == 0) // pilot run: remember the pivot sequence
+                        a.trace[inst * PLAN_TRACE_MAX + (tcnt++ & (PLAN_TRACE_MAX - 1))] = s.perm;
                 } else {
                     LSync::forward(ts, Jp, yp, s.perm);
                 }

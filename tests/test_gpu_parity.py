@@ -644,3 +644,57 @@ def test_sparse_kernel_dc_sweep_and_record_stride(oracle_mod):
         assert np.array_equal(rs.t[i, :kept], rf.t[i, 0:3 * kept:3])
         assert np.array_equal(rs.x[i, :kept], rf.x[i, 0:3 * kept:3])
     assert np.array_equal(rs.x_final, rf.x_final)
+
+
+# ------------------------------------------------------------------------------------------------------
+# learned elimination plans (thread per instance, n <= 16, .op / .dc) against the dense kernels
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which,rel", [("proj1_nl", 0.1), ("proj1_nl", 0.45), ("proj1", 0.1), ("proj2", 0.3), ("npn_test", 0.3),
+                                       ("nmos_test", 0.3), ("r_d_direct", 0.3), ("v_divider", 0.3)])
+@pytest.mark.parametrize("lanes", [0, 1, 2])
+def test_plan_kernel_equals_dense_kernel_bitwise_op(which, rel, lanes):
+    """The plan interpreter executes the reference's operations on the structural non-zeros only; instances whose
+    pivot sequence has no plan (wide Monte-Carlo spread) or that meet a zero / non-finite pivot go to the dense kernel.
+    Every output must compare equal to the dense kernel's, and so must the counters."""
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else load(which)
+    B = 3000
+    vals, fns = nl.monte_carlo(circ, B, rel=rel)
+    outs = []
+    for plan in (1, 0):
+        be = BatchEngine(circ)
+        be.set_option("plan", plan)
+        be.set_option("plan_lanes", lanes)
+        be.set_params(vals, fns)
+        r = be.run_op()
+        c = be.counters()
+        outs.append((be.variant, c, (r.status, r.n_iters, r.x, c["solve_points"], c["newton_iters"], c["lu_factor"])))
+        r2 = be.run_op()  # second call: plans are cached in the handle
+        assert np.array_equal(r2.x, r.x, equal_nan=True) and np.array_equal(r2.n_iters, r.n_iters)
+    assert outs[0][0].startswith("plan") and not outs[1][0].startswith("plan"), (outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][2], outs[1][2]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert outs[0][1]["redo"] < B // 2, outs[0][1]
+
+
+def test_plan_kernel_equals_dense_kernel_bitwise_dc(oracle_mod):
+    circ = load("nmos_test")
+    C, Lp = 500, 24
+    width = 3.6 / C  # crosses the 3.48 V failure (Q18): those chains stop early
+    start = np.arange(C) * width
+    step = np.full(C, width / Lp)
+    stop = start + width - 0.25 * step
+    vals = np.broadcast_to(circ.vals, (C, circ.n_elems)).copy()
+    se = circ.elem_index("V01")
+    outs = []
+    for plan in (1, 0):
+        be = BatchEngine(circ)
+        be.set_option("plan", plan)
+        be.set_params(vals)
+        r = be.run_dc(se, start, stop, step, max_points=Lp)
+        c = be.counters()
+        outs.append((be.variant, (r.status, r.points_done, r.n_iters, r.x, c["solve_points"], c["newton_iters"])))
+    assert outs[0][0].startswith("plan") and not outs[1][0].startswith("plan"), (outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, None, se, start, stop, step, Lp, threads=8)
+    assert (outs[0][1][0] == st).all() and (outs[0][1][1] == done).all()
