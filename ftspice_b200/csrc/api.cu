@@ -12,6 +12,7 @@
 
 #include "../../include/ftsb.h"
 #include "compile.h"
+#include "jit.h"
 #include "solver_lanes.cuh"
 #include "solver_plan.cuh"
 #include "solver_sparse.cuh"
@@ -68,6 +69,12 @@ struct ftsb_circuit {
     int plan_state[2] = {0, 0}; // 0 = not tried, 1 = plans available, -1 = no usable plan
     int plan_opt = 1;           // 1: use the plan-interpreting kernels for n <= 16 (.op / .dc)
     int plan_lanes = 0;         // lanes per instance of those kernels (0 = automatic)
+    // per-topology specialised kernels (jit.h), one per analysis mode, generated from the plans
+    JitKernel jit[2];
+    int jit_state[2] = {0, 0}; // 0 = not tried, 1 = loaded, -1 = unavailable (NVRTC / driver missing, compile error)
+    int jit_occ[2] = {0, 0};
+    int jit_opt = 1;
+    std::string jit_msg;
     std::string err;
     std::string variant = "none";
     long long launches = 0;
@@ -512,6 +519,50 @@ int plan_plans(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, PlanPro
     return 0;
 }
 
+// per-topology kernel for (handle, mode): generate, compile and load once.  Returns true when it can be launched.
+bool ensure_jit(ftsb_circuit *c, int an)
+{
+    if (!c->jit_opt || !c->skip_refactor || c->plan_state[an] != 1) return false;
+    if (c->jit_state[an] != 0) return c->jit_state[an] == 1;
+    c->jit_state[an] = -1;
+    const PlanHost &ph = c->plan_host[an];
+    const std::string src = jit_source(c->comp, an, ph);
+    std::string cubin, err;
+    if (!jit_compile(src, cubin, err)) {
+        c->jit_msg = err;
+        return false;
+    }
+    const int smem = ph.S * 32 * 8;
+    if ((size_t)smem > c->smem_optin || !jit_load(cubin, smem, c->jit[an], err)) {
+        c->jit_msg = err;
+        return false;
+    }
+    c->jit_occ[an] = jit_occupancy(c->jit[an]);
+    if (c->jit_occ[an] < 1) {
+        c->jit_msg = "occupancy query failed";
+        jit_unload(c->jit[an]);
+        return false;
+    }
+    c->jit_state[an] = 1;
+    return true;
+}
+
+int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
+{
+    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+    const std::vector<int> &ib = c->comp.ints();
+    int sweep_slot = an == AN_DC ? ib[c->comp.off_src + 5 * a.sweep_src + 1] : 0;
+    const double *vals = a.vals, *fn = a.fn, *st = a.start, *sp = a.stop, *se = a.step;
+    long long batch = a.batch, max_points = a.max_points;
+    void *params[] = {&vals, &fn, &batch, &a.work, &a.counters, &a.x, &a.n_iters, &a.status, &a.redo_list, &a.redo_count,
+                      &st, &sp, &se, &max_points, &a.points_done, &sweep_slot};
+    const int grid = (int)std::max(1LL, std::min((a.batch + 31) / 32, (long long)c->jit_occ[an] * c->sm_count));
+    std::string err;
+    if (!jit_launch(c->jit[an], grid, (void *)c->stream, params, err)) return fail(c, FTSB_E_CUDA, err);
+    c->launches++;
+    return 0;
+}
+
 // one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
 // the dense / small-circuit kernels alone.  `dense_lanes`: the dense plan takes an external start-up solution.
 int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
@@ -519,7 +570,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
     LaunchPlan ps, pd;
     int fcap = 0, hist_global = 0;
     bool sparse = plan_sparse(c, an, a.batch, ps, fcap, hist_global) == 0;
-    bool planned = false;
+    bool planned = false, use_jit = false;
     if (!sparse && (an == AN_OP || an == AN_DC) && std::max(c->comp.n_start, 1) <= 16 && c->plan_opt && !c->force_generic &&
         !c->force_cta && !c->sparse && c->lanes <= 0 && a.batch >= 64) {
         if (c->plan_state[an] == 0) {
@@ -528,6 +579,12 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         }
         planned = plan_plans(c, an, a.batch, ps, a.plan) == 0;
         sparse = planned; // same launch protocol: first kernel + redo list + dense pass
+        if (planned && ensure_jit(c, an)) {
+            use_jit = true;
+            const PlanHost &ph = c->plan_host[an];
+            c->variant = "jit" + std::to_string(ph.K) + "n" + std::to_string(ph.n) + "/S" + std::to_string(ph.S) + "/r" +
+                         std::to_string(c->jit[an].regs) + "/occ" + std::to_string(c->jit_occ[an]);
+        }
     }
     const std::string sv = c->variant;
     int rc = plan_launch(c, an, a.batch, pd);
@@ -547,7 +604,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         as.redo_list = (long long *)c->redo.p;
         as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
-        rc = launch_kernel(c, ps, as);
+        rc = use_jit ? launch_jit(c, an, as) : launch_kernel(c, ps, as);
         if (rc) return rc;
         a.in_list = as.redo_list;
         a.in_count = as.redo_count;
@@ -724,6 +781,8 @@ void ftsb_destroy(ftsb_circuit *c)
                       &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
                       &c->s_st, &c->redo, &c->plan_buf[0], &c->plan_buf[1], &c->trace};
     for (DevBuf *b : bufs) b->release();
+    jit_unload(c->jit[0]);
+    jit_unload(c->jit[1]);
     delete c;
 }
 
@@ -749,6 +808,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->plan_opt = value ? 1 : 0;
     else if (!strcmp(name, "plan_lanes"))
         c->plan_lanes = (int)value;
+    else if (!strcmp(name, "jit"))
+        c->jit_opt = value ? 1 : 0;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
@@ -1161,4 +1222,53 @@ extern "C" double ftsb_measure_fp64_tflops(int device)
     cudaEventDestroy(e1);
     cudaFree(out);
     return best;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// diagnostics (not part of include/ftsb.h): generate + compile the per-topology kernel without a GPU
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ftsb_debug_jit(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t n_start, const int32_t *row_class,
+                              int32_t an, const uint64_t *perms, const int64_t *counts, int32_t n_perms, const char *src_path,
+                              char *log, int32_t log_cap)
+{
+    Compiled comp;
+    std::string err;
+    auto say = [&](const std::string &m) {
+        if (log && log_cap > 0) snprintf(log, (size_t)log_cap, "%s", m.c_str());
+    };
+    if (!compile_circuit(reinterpret_cast<const ElemDesc *>(elems), n_elems, n_run, n_start, row_class, 0, comp, err)) {
+        say(err);
+        return -1;
+    }
+    const ModeOff &mo = comp.mode[an];
+    const std::vector<int> &ib = comp.ints();
+    std::vector<int> jdst(ib.begin() + mo.J_full.dst, ib.begin() + mo.J_full.dst + mo.J_full.n_dst);
+    std::vector<std::pair<uint64_t, long long>> pv;
+    for (int i = 0; i < n_perms; ++i) pv.push_back({perms[i], (long long)counts[i]});
+    PlanHost ph;
+    if (!build_plans(mo.n, jdst, pv, ph)) {
+        say("build_plans failed");
+        return -2;
+    }
+    const std::string src = jit_source(comp, an, ph);
+    if (src_path) {
+        if (FILE *f = fopen(src_path, "w")) {
+            fwrite(src.data(), 1, src.size(), f);
+            fclose(f);
+        }
+    }
+    std::string cubin;
+    if (!jit_compile(src, cubin, err)) {
+        say(err);
+        return -3;
+    }
+    if (src_path) {
+        if (FILE *f = fopen((std::string(src_path) + ".cubin").c_str(), "wb")) {
+            fwrite(cubin.data(), 1, cubin.size(), f);
+            fclose(f);
+        }
+    }
+    say("ok K=" + std::to_string(ph.K) + " S=" + std::to_string(ph.S) + " cubin " + std::to_string(cubin.size()) + " bytes; " + err);
+    return 0;
 }

@@ -9,6 +9,8 @@
 // strictly largest |a| among the structural candidates); if another row wins it switches to the plan that shares
 // the pivots so far and takes that row next, or — unknown sequence — gives the instance to the dense kernel.
 #pragma once
+#include <cuda_runtime.h> // int4
+
 #include <cstdint>
 #include <utility>
 #include <vector>

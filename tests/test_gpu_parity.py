@@ -651,8 +651,8 @@ def test_sparse_kernel_dc_sweep_and_record_stride(oracle_mod):
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("which,rel", [("proj1_nl", 0.1), ("proj1_nl", 0.45), ("proj1", 0.1), ("proj2", 0.3), ("npn_test", 0.3),
                                        ("nmos_test", 0.3), ("r_d_direct", 0.3), ("v_divider", 0.3)])
-@pytest.mark.parametrize("lanes", [0, 1, 2])
-def test_plan_kernel_equals_dense_kernel_bitwise_op(which, rel, lanes):
+@pytest.mark.parametrize("mode", ["jit", "plan0", "plan1", "plan2"])
+def test_plan_kernel_equals_dense_kernel_bitwise_op(which, rel, mode):
     """The plan interpreter executes the reference's operations on the structural non-zeros only; instances whose
     pivot sequence has no plan (wide Monte-Carlo spread) or that meet a zero / non-finite pivot go to the dense kernel.
     Every output must compare equal to the dense kernel's, and so must the counters."""
@@ -663,20 +663,22 @@ def test_plan_kernel_equals_dense_kernel_bitwise_op(which, rel, lanes):
     for plan in (1, 0):
         be = BatchEngine(circ)
         be.set_option("plan", plan)
-        be.set_option("plan_lanes", lanes)
+        be.set_option("jit", 1 if mode == "jit" else 0)
+        be.set_option("plan_lanes", 0 if mode == "jit" else int(mode[4:]))
         be.set_params(vals, fns)
         r = be.run_op()
         c = be.counters()
         outs.append((be.variant, c, (r.status, r.n_iters, r.x, c["solve_points"], c["newton_iters"], c["lu_factor"])))
         r2 = be.run_op()  # second call: plans are cached in the handle
         assert np.array_equal(r2.x, r.x, equal_nan=True) and np.array_equal(r2.n_iters, r.n_iters)
-    assert outs[0][0].startswith("plan") and not outs[1][0].startswith("plan"), (outs[0][0], outs[1][0])
+    assert outs[0][0].startswith("jit" if mode == "jit" else "plan") and outs[1][0].startswith("sync"), (outs[0][0], outs[1][0])
     for a, b in zip(outs[0][2], outs[1][2]):
         assert np.array_equal(a, b, equal_nan=True)
     assert outs[0][1]["redo"] < B // 2, outs[0][1]
 
 
-def test_plan_kernel_equals_dense_kernel_bitwise_dc(oracle_mod):
+@pytest.mark.parametrize("jit", [1, 0])
+def test_plan_kernel_equals_dense_kernel_bitwise_dc(jit, oracle_mod):
     circ = load("nmos_test")
     C, Lp = 500, 24
     width = 3.6 / C  # crosses the 3.48 V failure (Q18): those chains stop early
@@ -689,11 +691,12 @@ def test_plan_kernel_equals_dense_kernel_bitwise_dc(oracle_mod):
     for plan in (1, 0):
         be = BatchEngine(circ)
         be.set_option("plan", plan)
+        be.set_option("jit", jit)
         be.set_params(vals)
         r = be.run_dc(se, start, stop, step, max_points=Lp)
         c = be.counters()
         outs.append((be.variant, (r.status, r.points_done, r.n_iters, r.x, c["solve_points"], c["newton_iters"])))
-    assert outs[0][0].startswith("plan") and not outs[1][0].startswith("plan"), (outs[0][0], outs[1][0])
+    assert outs[0][0].startswith("jit" if jit else "plan") and outs[1][0].startswith("sync"), (outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(a, b, equal_nan=True)
     st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, None, se, start, stop, step, Lp, threads=8)
