@@ -429,22 +429,25 @@ def main():
         e2e_v = pts_all * args.steps / (e2e_ms_total * 1e-3)
         fm = flop_model(circ, wl["kind"] if wl["kind"] == "op" else "run")
         ref_flops = cnt["newton_iters"] * (fm["factor"] + fm["solve"] + fm["rest"])
-        sparse = be.variant.startswith("spw")
+        sparse = be.variant.startswith(("spw", "jit", "plan"))  # kernels that skip structural zeros: device / plan flop counts
         if sparse:  # structure-exploiting kernel: flops it actually executed (device counter) + the per-iteration rest
             exec_flops = cnt["sparse_flops"] + cnt["newton_iters"] * fm["rest_exec"]
         else:
             exec_flops = cnt["lu_factor"] * fm["factor"] + cnt["lu_solve"] * fm["solve"] + cnt["newton_iters"] * fm["rest_exec"]
         kern_ms = float(np.mean(ms_dev))  # events bracket the step's launches (one kernel for .op/.dc; start-up + run for .tran)
         v0 = be.variant.split("/")[0]
-        kname = ("k_spw" if v0.startswith("spw") else "k_sync" if v0.startswith(("sync", "zskip")) else
+        kname = ("ftsb_jit (NVRTC, per topology)" if v0.startswith("jit") else "k_plan" if v0.startswith("plan") else
+                 "k_spw" if v0.startswith("spw") else "k_sync" if v0.startswith(("sync", "zskip")) else
                  "k_lanes" if v0.startswith("lanes") else "k_warp" if "r_n" in v0 else
                  "k_cta" if v0.startswith("cta") else "k_subwarp")
+        ncu_extra = {}
         traffic = None  # dram bytes per launch of that kernel from the committed ncu capture (profiles/traffic.json)
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             ent = tj.get(args.workload, {})
             if ent.get("variant_prefix") and be.variant.startswith(ent["variant_prefix"]) and args.scale == 1.0:
                 traffic = ent["dram_bytes_per_launch"]
+                ncu_extra = {k: ent[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warp_instructions_per_launch") if k in ent}
         except Exception:
             pass
         fp64_peak = float(L.ftsb_measure_fp64_tflops(local_rank))
@@ -480,6 +483,7 @@ def main():
                                         "cap it at 0.5 of this FMA peak",
                          "newton_iters_per_launch": cnt["newton_iters"], "lu_factor_per_launch": cnt["lu_factor"],
                          "lu_solve_per_launch": cnt["lu_solve"], "redo_instances": cnt.get("redo", 0),
+                         "ncu": ncu_extra or None,
                          "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
                                  "algorithmic_bytes_per_launch": alg_bytes,

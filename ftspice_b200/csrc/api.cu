@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,8 @@ struct ftsb_circuit {
     int jit_state[2] = {0, 0}; // 0 = not tried, 1 = loaded, -1 = unavailable (NVRTC / driver missing, compile error)
     int jit_occ[2] = {0, 0};
     int jit_opt = 1;
+    int jit_min_blocks = 1; // __launch_bounds__(32, this): register cap of the generated kernel
+    int last_plan_an = -1;  // analysis mode of the last run when it used the plan / JIT kernels (flop accounting)
     std::string jit_msg;
     std::string err;
     std::string variant = "none";
@@ -526,11 +529,23 @@ bool ensure_jit(ftsb_circuit *c, int an)
     if (c->jit_state[an] != 0) return c->jit_state[an] == 1;
     c->jit_state[an] = -1;
     const PlanHost &ph = c->plan_host[an];
-    const std::string src = jit_source(c->comp, an, ph);
+    const std::string src = jit_source(c->comp, an, ph) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
     std::string cubin, err;
-    if (!jit_compile(src, cubin, err)) {
-        c->jit_msg = err;
-        return false;
+    {
+        // the same topology + plans give the same source: compile once per process
+        static std::mutex mu;
+        static std::map<std::string, std::string> cache;
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(src);
+        if (it != cache.end())
+            cubin = it->second;
+        else {
+            if (!jit_compile(src, cubin, err, c->jit_min_blocks)) {
+                c->jit_msg = err;
+                return false;
+            }
+            cache[src] = cubin;
+        }
     }
     const int smem = ph.S * 32 * 8;
     if ((size_t)smem > c->smem_optin || !jit_load(cubin, smem, c->jit[an], err)) {
@@ -579,6 +594,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         }
         planned = plan_plans(c, an, a.batch, ps, a.plan) == 0;
         sparse = planned; // same launch protocol: first kernel + redo list + dense pass
+        if (planned) c->last_plan_an = an;
         if (planned && ensure_jit(c, an)) {
             use_jit = true;
             const PlanHost &ph = c->plan_host[an];
@@ -625,6 +641,7 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
     FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
     std::string v_op, v_main;
     bool ext_start = false;
+    c->last_plan_an = -1;
     if (an == AN_TRAN) { // does the .tran kernel take its start-up solution (engine.rs:158-161) from an .op launch?
         LaunchPlan t;
         int fc = 0, hg = 0;
@@ -810,6 +827,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->plan_lanes = (int)value;
     else if (!strcmp(name, "jit"))
         c->jit_opt = value ? 1 : 0;
+    else if (!strcmp(name, "jit_min_blocks"))
+        c->jit_min_blocks = (int)value;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
@@ -1062,6 +1081,10 @@ int ftsb_get_counters(ftsb_circuit *c, ftsb_counters *out)
     out->rej_plte = (int64_t)h[CN_REJ_PLTE];
     out->redo = (int64_t)h[CN_REDO];
     out->sparse_flops = (int64_t)h[CN_FLOPS];
+    if (c->last_plan_an >= 0) { // plan / JIT kernels: flops of the factorisations and substitutions along the main plan
+        const PlanHost &ph = c->plan_host[c->last_plan_an];
+        out->sparse_flops = out->lu_factor * ph.flops_factor + out->lu_solve * ph.flops_solve;
+    }
     return 0;
 }
 

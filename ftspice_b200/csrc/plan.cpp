@@ -118,6 +118,11 @@ bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair
     out.n = n;
     out.coverage = total ? (double)covered / (double)total : 0.0;
 
+    for (int k = 0; k < n; ++k) { // executed flops along the most frequent plan
+        const StepBuild &sb = plans[0][k];
+        out.flops_factor += 1 + 3 * (long long)sb.mult.size() + 2 * (long long)sb.upd.size();
+        out.flops_solve += 1 + 2 * (long long)sb.bu.size();
+    }
     std::vector<int> rec((size_t)K * n * 4), cand, mult, upd, bu;
     for (int p = 0; p < K; ++p)
         for (int k = 0; k < n; ++k) {

@@ -38,6 +38,7 @@ struct PlanHost {
     std::vector<int> ibuf; // rec (16-byte aligned at offset 0), then the packed lists
     int off_rec = 0, off_cand = 0, off_mult = 0, off_upd = 0, off_bu = 0, off_next = 0, off_jdst = 0;
     double coverage = 0.0; // share of the pilot's factorisations whose pivot sequence has a plan
+    long long flops_factor = 0, flops_solve = 0; // floating-point operations of one factorisation / one back substitution (plan 0)
 };
 
 // jfull_dst: J_full destinations (row | col << 16) in J_full order; perms: (nibble-packed position -> row, count),
