@@ -68,6 +68,10 @@ struct ftsb_circuit {
     PlanHost plan_host[2];
     DevBuf plan_buf[2], trace;
     int plan_state[2] = {0, 0}; // 0 = not tried, 1 = plans available, -1 = no usable plan
+    std::map<unsigned long long, long long> plan_hist[2]; // traced pivot sequences and how often each occurred
+    int relearn_left[2] = {0, 0};                          // how many more times redo traces may extend the plans
+    bool redo_traced[2] = {false, false};                  // the last run's redo pass wrote a trace
+    int last_redo_an = -1;                                 // analysis whose redo count sits in the counters
     int plan_opt = 1;           // 1: use the plan-interpreting kernels for n <= 16 (.op / .dc)
     int plan_lanes = 0;         // lanes per instance of those kernels (0 = automatic)
     // per-topology specialised kernels (jit.h), one per analysis mode, generated from the plans
@@ -436,41 +440,99 @@ int launch_kernel(ftsb_circuit *c, const LaunchPlan &pl, RunArgs &a)
 // ---- learned elimination plans for small circuits (plan.h, solver_plan.cuh) ---------------------------------
 // First .op / .dc call of a handle: a pilot run of the dense kernel over the first PLAN_PILOT instances records the
 // pivot sequence of every factorisation; the host turns the most frequent sequences into plans.
-int learn_plans(ftsb_circuit *c, int an, const RunArgs &a)
+// histogram of traced pivot sequences -> plans on the device.  Returns true when usable plans exist.
+int rebuild_plans(ftsb_circuit *c, int an, bool &ok)
 {
-    c->plan_state[an] = -1;
-    LaunchPlan pd;
-    if (plan_lanes(c, an, std::min<long long>(a.batch, PLAN_PILOT), pd) != 0) return 0;
-    const long long sample = std::min<long long>(a.batch, PLAN_PILOT);
-    const size_t tb = (size_t)sample * PLAN_TRACE_MAX * 8;
-    FTSB_CUDA(c, c->trace.ensure(tb));
-    FTSB_CUDA(c, cudaMemsetAsync(c->trace.p, 0, tb, c->stream));
-    RunArgs ap = a;
-    ap.batch = sample;
-    ap.prog.lay = pd.lay;
-    ap.trace = (unsigned long long *)c->trace.p;
-    ap.in_list = nullptr;
-    ap.in_count = nullptr;
-    int rc = launch_kernel(c, pd, ap);
-    if (rc) return rc;
-    std::vector<unsigned long long> tr((size_t)sample * PLAN_TRACE_MAX);
-    FTSB_CUDA(c, cudaMemcpyAsync(tr.data(), c->trace.p, tb, cudaMemcpyDeviceToHost, c->stream));
-    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
-    // the pilot's counters must not leak into the caller's run
-    FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
-    std::map<unsigned long long, long long> hist;
-    for (unsigned long long v : tr)
-        if (v) ++hist[v];
+    ok = false;
     const ModeOff &mo = c->comp.mode[an];
     const std::vector<int> &ib = c->comp.ints();
     std::vector<int> jdst(ib.begin() + mo.J_full.dst, ib.begin() + mo.J_full.dst + mo.J_full.n_dst);
-    std::vector<std::pair<uint64_t, long long>> perms(hist.begin(), hist.end());
+    std::vector<std::pair<uint64_t, long long>> perms(c->plan_hist[an].begin(), c->plan_hist[an].end());
     PlanHost &ph = c->plan_host[an];
     if (!build_plans(mo.n, jdst, perms, ph)) return 0;
     FTSB_CUDA(c, c->plan_buf[an].ensure(ph.ibuf.size() * 4));
     FTSB_CUDA(c, cudaMemcpyAsync(c->plan_buf[an].p, ph.ibuf.data(), ph.ibuf.size() * 4, cudaMemcpyHostToDevice, c->stream));
     FTSB_CUDA(c, cudaStreamSynchronize(c->stream)); // ph.ibuf is pageable
-    c->plan_state[an] = 1;
+    ok = true;
+    return 0;
+}
+
+int read_trace(ftsb_circuit *c, int an, long long rows)
+{
+    if (rows <= 0) return 0;
+    std::vector<unsigned long long> tr((size_t)rows * PLAN_TRACE_MAX);
+    FTSB_CUDA(c, cudaMemcpyAsync(tr.data(), c->trace.p, tr.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (unsigned long long v : tr)
+        if (v) ++c->plan_hist[an][v];
+    return 0;
+}
+
+int learn_plans(ftsb_circuit *c, int an, const RunArgs &a)
+{
+    c->plan_state[an] = -1;
+    const long long sample = std::min<long long>(a.batch, PLAN_PILOT);
+    LaunchPlan pd;
+    if (plan_lanes(c, an, sample, pd) != 0) return 0;
+    const size_t tb = (size_t)PLAN_TRACE_ROWS * PLAN_TRACE_MAX * 8;
+    FTSB_CUDA(c, c->trace.ensure(tb));
+    FTSB_CUDA(c, cudaMemsetAsync(c->trace.p, 0, tb, c->stream));
+    // sample spread over the whole batch (list mode)
+    std::vector<long long> lst((size_t)sample + 1);
+    for (long long i = 0; i < sample; ++i) lst[(size_t)i] = i * a.batch / sample;
+    unsigned long long cnt = (unsigned long long)sample;
+    FTSB_CUDA(c, c->redo.ensure((size_t)std::max<long long>(a.batch, sample) * 8 + 8));
+    FTSB_CUDA(c, cudaMemcpyAsync(c->redo.p, lst.data(), (size_t)sample * 8, cudaMemcpyHostToDevice, c->stream));
+    FTSB_CUDA(c, cudaMemcpyAsync((unsigned long long *)c->counters.p + CN_REDO, &cnt, 8, cudaMemcpyHostToDevice, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream)); // lst / cnt are pageable
+    RunArgs ap = a;
+    ap.prog.lay = pd.lay;
+    ap.trace = (unsigned long long *)c->trace.p;
+    ap.trace_rows = PLAN_TRACE_ROWS;
+    ap.in_list = (const long long *)c->redo.p;
+    ap.in_count = (const unsigned long long *)c->counters.p + CN_REDO;
+    int rc = launch_kernel(c, pd, ap);
+    if (rc) return rc;
+    rc = read_trace(c, an, sample);
+    if (rc) return rc;
+    // the pilot's counters must not leak into the caller's run
+    FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
+    bool ok = false;
+    rc = rebuild_plans(c, an, ok);
+    if (rc) return rc;
+    if (ok) c->plan_state[an] = 1;
+    c->relearn_left[an] = 3;
+    return 0;
+}
+
+// Instances the previous run handed to the dense kernel were traced: add their pivot sequences to the plans.
+int relearn_plans(ftsb_circuit *c, int an)
+{
+    if (c->plan_state[an] != 1 || c->relearn_left[an] <= 0 || !c->redo_traced[an]) return 0;
+    c->redo_traced[an] = false;
+    unsigned long long n_redo = 0;
+    FTSB_CUDA(c, cudaMemcpyAsync(&n_redo, (unsigned long long *)c->counters.p + CN_REDO, 8, cudaMemcpyDeviceToHost, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_redo == 0) {
+        c->relearn_left[an] = 0; // the plans cover the workload
+        return 0;
+    }
+    c->relearn_left[an]--;
+    const size_t before = c->plan_hist[an].size();
+    int rc = read_trace(c, an, std::min<long long>((long long)n_redo, PLAN_TRACE_ROWS));
+    if (rc) return rc;
+    if (c->plan_hist[an].size() == before) return 0; // nothing new (e.g. zero pivots: the dense kernel's job)
+    const int k_before = c->plan_host[an].K;
+    bool ok = false;
+    rc = rebuild_plans(c, an, ok);
+    if (rc) return rc;
+    if (!ok) {
+        c->plan_state[an] = -1;
+        return 0;
+    }
+    (void)k_before; // new plans (or a new order): the specialised kernel is regenerated on demand
+    jit_unload(c->jit[an]);
+    c->jit_state[an] = 0;
     return 0;
 }
 
@@ -624,6 +686,13 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         if (rc) return rc;
         a.in_list = as.redo_list;
         a.in_count = as.redo_count;
+        if (planned && c->relearn_left[an] > 0) { // the dense redo pass records what the plans did not cover
+            FTSB_CUDA(c, cudaMemsetAsync(c->trace.p, 0, (size_t)PLAN_TRACE_ROWS * PLAN_TRACE_MAX * 8, c->stream));
+            a.trace = (unsigned long long *)c->trace.p;
+            a.trace_rows = PLAN_TRACE_ROWS;
+            c->redo_traced[an] = true;
+        }
+        c->last_redo_an = an;
     }
     a.prog.lay = pd.lay;
     rc = launch_kernel(c, pd, a);
@@ -638,6 +707,11 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
     a.work = (unsigned long long *)c->work.p;
     a.counters = (unsigned long long *)c->counters.p;
     a.skip_refactor = c->skip_refactor;
+    if ((an == AN_OP || an == AN_DC) && c->last_redo_an == an) { // before the counters are cleared: did the plans miss instances?
+        int rcl = relearn_plans(c, an);
+        if (rcl) return rcl;
+    }
+    c->last_redo_an = -1;
     FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
     std::string v_op, v_main;
     bool ext_start = false;

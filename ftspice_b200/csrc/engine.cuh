@@ -69,7 +69,8 @@ struct RunArgs {
     const unsigned long long *in_count;
     // learned elimination plans (solver_plan.cuh) and, in the pilot run that learns them, the pivot-sequence trace
     PlanProg plan;
-    unsigned long long *trace; // [batch][PLAN_TRACE_MAX] nibble-packed position -> row of every factorisation (ring)
+    unsigned long long *trace; // [trace_rows][PLAN_TRACE_MAX] nibble-packed position -> row of every factorisation (ring)
+    long long trace_rows;      // rows available: one per work-list position
 };
 
 // next work item of a persistent kernel: an instance index, or -1 when the work is exhausted

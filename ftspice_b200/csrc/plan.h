@@ -19,7 +19,8 @@ namespace ftsb {
 
 constexpr int PLAN_MAX = 8;         // plans kept per analysis mode
 constexpr int PLAN_TRACE_MAX = 128; // pivot sequences recorded per pilot instance (ring)
-constexpr int PLAN_PILOT = 512;     // pilot instances
+constexpr int PLAN_PILOT = 1024;    // pilot instances, spread over the batch
+constexpr int PLAN_TRACE_ROWS = 4096; // rows of the trace buffer (pilot sample / traced redo instances)
 
 // device view (pointers into one int buffer)
 struct PlanProg {

@@ -789,7 +789,8 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
     long long k = 0, count = 0;
     double dc_start = 0.0, dc_step = 0.0;
     const int sweep_slot = AN == AN_DC ? __ldg(&P.src[5 * a.sweep_src + 1]) : 0;
-    int tcnt = 0; // factorisations of the current instance recorded in the pivot trace (pilot runs only)
+    int tcnt = 0; // factorisations of the current instance recorded in the pivot trace (pilot / redo runs only)
+    long long tidx = 0;
 
     for (;;) {
         // ---------------- transitions ----------------
@@ -803,6 +804,7 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
                 const unsigned below = need & ((1u << tl.slot) - 1u);
                 if (phase == PH_FETCH) {
                     inst = first + __popc(below);
+                    tidx = inst; // trace row: the position in the work list
                     if (a.in_list) inst = (unsigned long long)inst < *a.in_count ? a.in_list[inst] : a.batch; // list mode
                     tcnt = 0;
                 }
@@ -894,8 +896,8 @@ __global__ void __launch_bounds__(32) k_sync(const __grid_constant__ RunArgs a)
                     LSync::factor(ts, Jp, yp, s.perm);
                     s.jvalid = linear;
                     if (solving) cn.c[CN_FACTOR]++;
-                    if (a.trace && solving && do_factor && ts.rank == 0) // pilot run: remember the pivot sequence
-                        a.trace[inst * PLAN_TRACE_MAX + (tcnt++ & (PLAN_TRACE_MAX - 1))] = s.perm;
+                    if (a.trace && solving && do_factor && ts.rank == 0 && tidx < a.trace_rows) // remember the pivot sequence
+                        a.trace[tidx * PLAN_TRACE_MAX + (tcnt++ & (PLAN_TRACE_MAX - 1))] = s.perm;
                 } else {
                     LSync::forward(ts, Jp, yp, s.perm);
                 }
