@@ -65,7 +65,9 @@ enum {
 enum {
     FTSB_MEM_HOST = 0,  /* host pointers; the call copies in/out and returns when results are in place */
     FTSB_MEM_DEVICE = 1 /* device pointers on the handle's device; the call only enqueues work on the
-                           handle's stream and returns; use ftsb_sync() */
+                           handle's stream and returns; use ftsb_sync().  Exception: the first .op / .dc calls
+                           of a handle on a small circuit learn elimination plans from a pilot run and compile
+                           a per-topology kernel (about a second, once); those calls synchronise the stream */
 };
 
 /* layout of the per-instance parameter arrays handed to ftsb_set_params */
