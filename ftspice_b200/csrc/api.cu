@@ -90,6 +90,7 @@ struct ftsb_circuit {
     int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
     int lanes = 0;         // >0: lanes per instance requested for the dense small-circuit kernels (if built)
     int sparse_warp = 1;   // 1 (default): structure-exploiting warp-per-instance kernels for n > 16
+    int slots_global = 1;  // 1: large circuits keep the slot table and the solution vectors in L2-resident global scratch
     int fill_cap = 0;      // >0: run-time fill-in pool entries per instance of those kernels (0 = automatic)
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
@@ -373,6 +374,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     // run-time fill-in pool: partial pivoting may leave the predicted structure; an instance that exhausts the pool
     // goes to the dense kernels.  Halve until one warp fits.
     fcap = c->fill_cap > 0 ? c->fill_cap : std::max(32, nnz / 2);
+    if (c->fill_cap <= 0 && an != AN_OP) fcap = std::min(fcap, 128); // companion conductances keep .tran / .dc pivots near the prediction
     fcap = (fcap + 1) & ~1;
     if (n >= 0xfff0) return 1; // u16 indices
     if (nnz + fcap >= 0xfff0) fcap = (0xfff0 - nnz - 2) & ~1;
@@ -380,13 +382,15 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     KernelFn fn = sparse_kernel(an);
     const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
     SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
-    if (an == AN_TRAN && T.bytes > 32 * 1024) { // large circuit: per-step history to global scratch (more warps per SM)
-        hist_global = 1;
-        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, true, true);
+    if (T.bytes > 32 * 1024) { // large circuit: per-step history (and optionally the slot table) to global scratch
+        // 1: per-step history, 2: slot table, 4: x / x_new / x_proposed / b -> L2-resident global scratch; what stays in
+        // shared memory is what the sequential elimination touches (matrix entries, rhs, structure)
+        hist_global = (an == AN_TRAN ? 1 : 0) | (c->slots_global ? 6 : 0);
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global);
     }
     while (stat + ((T.bytes + 15) & ~(size_t)15) > c->smem_optin && fcap > 64 && c->fill_cap <= 0) {
         fcap = (fcap / 2 + 1) & ~1;
-        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global != 0);
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global);
     }
     const size_t per_warp = (T.bytes + 15) & ~(size_t)15;
     int best_w = 0, best_occ = 0;
@@ -424,7 +428,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     pl.grid = (int)std::max(1LL, std::min(need, (long long)best_occ * c->sm_count));
     pl.scratch_bytes = (size_t)pl.grid * best_w * T.hist_doubles * 8;
     c->variant = "spw_n" + std::to_string(n) + "/nnz" + std::to_string(nnz - mo.sp.n_pred) + "+" + std::to_string(mo.sp.n_pred) +
-                 "/fill" + std::to_string(fcap) + (hist_global ? "/hg" : "") + "/occ" + std::to_string(best_occ * best_w);
+                 "/fill" + std::to_string(fcap) + (hist_global ? "/hg" + std::to_string(hist_global) : "") + "/occ" + std::to_string(best_occ * best_w);
     return 0;
 }
 
@@ -678,7 +682,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         RunArgs as = a;
         as.prog.lay = ps.lay;
         as.prog.op.sp.fcap = as.prog.dc.sp.fcap = as.prog.tran.sp.fcap = fcap;
-        as.prog.tran.sp.hist_global = hist_global;
+        as.prog.op.sp.hist_global = as.prog.dc.sp.hist_global = as.prog.tran.sp.hist_global = hist_global;
         as.redo_list = (long long *)c->redo.p;
         as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
@@ -905,6 +909,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->jit_min_blocks = (int)value;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "slots_global"))
+        c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
     else

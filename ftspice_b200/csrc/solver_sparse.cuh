@@ -28,7 +28,11 @@ constexpr int ST_REDO = 100; // internal: never returned to the caller
 
 struct SpLayout {
     int osv, oy, ox, oxn, oxp, obv, oval, oprev, ostate, oring, doubles; // in doubles
-    int hist_doubles; // > 0: state + ring live in global scratch (that many doubles per resident warp), not here
+    int hist_doubles; // > 0: that many doubles per resident warp live in global scratch, not here: the per-step history
+                      // (state + ring; bit 0 of `glob`) and / or the slot table (bit 1)
+    int val_global;   // the slot table is in the global region (offset oval there)
+    int vec_global;   // x, x_new, x_proposed and b are in the global region (bit 2); tval then has its own shared array
+    int otval;
     int ofr, ofc, ofnr, ofnc, orh, och, opos, opiv, ope, otcol, halfs;      // in u16 after the doubles
     int words;                                                               // fill signature: one u32 per row, after the u16s
     int fcap;
@@ -36,7 +40,7 @@ struct SpLayout {
 };
 
 __host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_slots, int n_dyn, int n_src, bool tran,
-                                              bool hist_global = false)
+                                              int glob = 0)
 {
     SpLayout t;
     int o = 0;
@@ -48,21 +52,37 @@ __host__ __device__ inline SpLayout sp_layout(int n, int nnz, int fcap, int n_sl
     t.fcap = fcap;
     t.osv = take(nnz + fcap);
     t.oy = take(n);
-    t.ox = take(n);
-    t.oxn = take(n);
-    t.oxp = take(n);
-    t.obv = take(n); // b of the current solve (the residual subtracts it every iteration)
-    t.oval = take(n_slots);
+    int go = 0; // offsets inside the global region
+    auto takeg = [&](int c) {
+        int r = go;
+        go += (c + 1) & ~1;
+        return r;
+    };
+    t.val_global = (glob & 2) ? 1 : 0;
+    t.vec_global = (glob & 4) ? 1 : 0;
+    if (t.vec_global) { // only the rhs (read and written inside the sequential elimination) stays on chip
+        t.ox = takeg(n);
+        t.oxn = takeg(n);
+        t.oxp = takeg(n);
+        t.obv = takeg(n);
+        t.otval = take(n);
+    } else {
+        t.ox = take(n);
+        t.oxn = take(n);
+        t.oxp = take(n);
+        t.obv = take(n); // b of the current solve (the residual subtracts it every iteration)
+        t.otval = t.oxn; // scratch during a factorisation: x_new is dead then
+    }
+    t.oval = t.val_global ? takeg(n_slots) : take(n_slots);
     t.oprev = take(tran ? 3 * n_src : 0);
-    t.hist_doubles = 0;
-    if (tran && hist_global) {
-        t.ostate = 0;
-        t.oring = (2 * n_dyn + 1) & ~1;
-        t.hist_doubles = t.oring + ((3 * n + 1) & ~1);
+    if (tran && (glob & 1)) {
+        t.ostate = takeg(2 * n_dyn);
+        t.oring = takeg(3 * n);
     } else {
         t.ostate = take(tran ? 2 * n_dyn : 0);
         t.oring = take(tran ? 3 * n : 0);
     }
+    t.hist_doubles = go;
     t.doubles = o;
     int h = 0;
     auto takeh = [&](int c) {
@@ -137,7 +157,7 @@ struct SparseWarpSolver {
         st.lmap = st.rent + nnz;
         in.fcap = fcap;
         in.sv = w.J.p;
-        in.tval = w.xn.p; // scratch during a factorisation: x_new is dead then
+        in.tval = w.A.p; // pivot-row scratch of a factorisation (aliases x_new unless the vectors live in global memory)
         u16 *hb = reinterpret_cast<u16 *>(w.piv.p);
         in.fr = hb;
         in.fc = in.fr + fcap;
@@ -599,26 +619,28 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     }
     __syncthreads();
     const int fcap = M.sp.fcap;
-    const SpLayout T = sp_layout(n, nnz, fcap, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN, M.sp.hist_global != 0);
+    const SpLayout T = sp_layout(n, nnz, fcap, P.n_slots, P.n_dyn, P.n_src, AN == AN_TRAN, M.sp.hist_global);
     unsigned char *wb = smem_raw + sp_static_bytes(n, nnz, M.sp.n_long) + (size_t)(threadIdx.x >> 5) * ((T.bytes + 15) & ~(size_t)15);
     double *base = reinterpret_cast<double *>(wb);
     Ws w;
     w.ld = n; // stride of the history ring
-    w.A.p = nullptr;
     w.J.p = base + T.osv;
     w.r.p = base + T.oy;
-    w.x.p = base + T.ox;
-    w.xn.p = base + T.oxn;
-    w.xp.p = base + T.oxp;
-    w.b.p = base + T.obv;
-    w.val.p = base + T.oval;
     w.prev.p = AN == AN_TRAN ? base + T.oprev : nullptr;
     {
         // per-step history (C/L state, last three accepted x): shared memory, or — large circuits — a global
         // scratch row per resident warp (touched once per accepted step, coalesced)
-        double *hb = T.hist_doubles ? a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles : base;
-        w.state.p = hb + T.ostate;
-        w.ring.p = hb + T.oring;
+        double *gb = a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles;
+        const bool hist_g = AN == AN_TRAN && (M.sp.hist_global & 1);
+        w.state.p = (hist_g ? gb : base) + T.ostate;
+        w.ring.p = (hist_g ? gb : base) + T.oring;
+        w.val.p = (T.val_global ? gb : base) + T.oval; // large slot tables: L2-resident scratch (more warps per SM)
+        double *vb = T.vec_global ? gb : base;
+        w.x.p = vb + T.ox;
+        w.xn.p = vb + T.oxn;
+        w.xp.p = vb + T.oxp;
+        w.b.p = vb + T.obv;
+        w.A.p = base + T.otval; // (the dense A is not kept by this solver: the field carries the pivot-row scratch)
     }
     w.piv.p = reinterpret_cast<int *>(base + T.doubles);
     w.aux = reinterpret_cast<const int *>(smem_raw);
