@@ -90,6 +90,8 @@ struct ftsb_circuit {
     int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
     int lanes = 0;         // >0: lanes per instance requested for the dense small-circuit kernels (if built)
     int sparse_warp = 1;   // 1 (default): structure-exploiting warp-per-instance kernels for n > 16
+    int windowed = 1;      // 1: the sparse kernel eliminates windows of independent columns at once when the predicted
+                           // structure allows it; 2: always try; 0: never
     int slots_global = 1;  // 1: large circuits keep the slot table and the solution vectors in L2-resident global scratch
     int fill_cap = 0;      // >0: run-time fill-in pool entries per instance of those kernels (0 = automatic)
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
@@ -151,6 +153,8 @@ ModeProg dev_mode(const int *base, const ModeOff &o)
     m.sp.n_pred = o.sp.n_pred;
     m.sp.fcap = 0;
     m.sp.hist_global = 0;
+    m.sp.windowed = 0;
+    m.sp.pad3 = 0;
     m.sp.cptr = base + o.sp.cptr;
     m.sp.erow = base + o.sp.erow;
     m.sp.rptr = base + o.sp.rptr;
@@ -428,7 +432,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     pl.grid = (int)std::max(1LL, std::min(need, (long long)best_occ * c->sm_count));
     pl.scratch_bytes = (size_t)pl.grid * best_w * T.hist_doubles * 8;
     c->variant = "spw_n" + std::to_string(n) + "/nnz" + std::to_string(nnz - mo.sp.n_pred) + "+" + std::to_string(mo.sp.n_pred) +
-                 "/fill" + std::to_string(fcap) + (hist_global ? "/hg" + std::to_string(hist_global) : "") + "/occ" + std::to_string(best_occ * best_w);
+                 "/fill" + std::to_string(fcap) + (hist_global ? "/hg" + std::to_string(hist_global) : "") + (c->windowed && mo.sp.window_hint >= 4 ? "/w" + std::to_string(mo.sp.window_hint) : "") + "/occ" + std::to_string(best_occ * best_w);
     return 0;
 }
 
@@ -683,6 +687,9 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         as.prog.lay = ps.lay;
         as.prog.op.sp.fcap = as.prog.dc.sp.fcap = as.prog.tran.sp.fcap = fcap;
         as.prog.op.sp.hist_global = as.prog.dc.sp.hist_global = as.prog.tran.sp.hist_global = hist_global;
+        // windows pay when the predicted structure lets several columns go at once (a rail-coupled chain: 32; a ladder: 1)
+        as.prog.op.sp.windowed = as.prog.dc.sp.windowed = as.prog.tran.sp.windowed =
+            (c->windowed == 2 || (c->windowed == 1 && c->comp.mode[an].sp.window_hint >= 4)) ? 1 : 0;
         as.redo_list = (long long *)c->redo.p;
         as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
@@ -909,6 +916,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->jit_min_blocks = (int)value;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "windowed"))
+        c->windowed = (int)value;
     else if (!strcmp(name, "slots_global"))
         c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))

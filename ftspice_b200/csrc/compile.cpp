@@ -378,6 +378,7 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
             }
             std::vector<std::map<int, bool>> work = rows;
             std::vector<int> pos(std::max(n, 1)), piv(std::max(n, 1));
+            std::vector<char> noswap(std::max(n, 1), 0);
             for (int i = 0; i < n; ++i) pos[i] = piv[i] = i;
             for (int k = 0; k < n; ++k) {
                 int P = -1, bestpos = 1 << 30;
@@ -397,6 +398,7 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
                 }
                 if (P < 0) continue; // structurally singular column: nothing to predict
                 const int rk = piv[k], pp = pos[P];
+                noswap[k] = pp == k;
                 piv[k] = P;
                 piv[pp] = rk;
                 pos[P] = k;
@@ -444,6 +446,25 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
                         for (const Con *c : it->second)
                             if (c->phase == ph) g.con.push_back((int)c->word);
                 g.ptr.push_back((int)g.con.size());
+            }
+            {
+                // how many consecutive columns the windowed elimination (solver_sparse.cuh) could take at once under the
+                // predicted pivots: a window ends at a swap or where an earlier pivot row of the window holds the column
+                int windows = 0;
+                for (int k0 = 0; k0 < n;) {
+                    int ext = 0;
+                    for (int l = 0; l < 32 && k0 + l < n; ++l) {
+                        const int k = k0 + l;
+                        bool okc = noswap[k] != 0;
+                        for (int kp = k0; kp < k && okc; ++kp)
+                            if (work[piv[kp]].count(k)) okc = false;
+                        if (!okc) break;
+                        ++ext;
+                    }
+                    k0 += std::max(ext, 1);
+                    ++windows;
+                }
+                o.sp.window_hint = windows ? n / windows : 0;
             }
             o.sp.nnz = (int)erow.size();
             o.sp.n_pred = n_pred;

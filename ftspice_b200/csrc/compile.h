@@ -20,7 +20,7 @@ struct GatherOff {
 };
 
 struct SparseOff {
-    int nnz = 0, n_pred = 0, cptr = 0, erow = 0, rptr = 0, rcol = 0, rent = 0, n_long = 0, rlong = 0, lmap = 0;
+    int nnz = 0, n_pred = 0, cptr = 0, erow = 0, rptr = 0, rcol = 0, rent = 0, n_long = 0, rlong = 0, lmap = 0, window_hint = 0;
     GatherOff S;
 };
 

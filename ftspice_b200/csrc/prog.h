@@ -56,6 +56,8 @@ struct SparseProg {
     const int *rptr; // [n + 1] row-ordered view: the t-th entry of row r, t in [rptr[r], rptr[r + 1]), columns ascending
     const int *rcol; // [nnz]   its column
     const int *rent; // [nnz]   its entry index e
+    int windowed;    // the launcher's switch for the windowed elimination (solver_sparse.cuh)
+    int pad3;
     int n_long;      // rows with many entries get a direct column -> entry map (at most SP_MAX_LONG of them)
     int pad2;
     const int *rlong; // [n]  index of the row's map, or -1

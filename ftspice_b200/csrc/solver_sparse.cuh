@@ -123,6 +123,7 @@ struct SpInst {
     u16 *fr, *fc, *fnr, *fnc, *rhead, *chead, *pos, *piv, *pe, *tcol;
     unsigned *sig; // bit (j & 31) of sig[r]: row r may hold a run-time fill-in entry in a column congruent to j
     int fcap;
+    int windowed; // try to eliminate windows of independent columns at once
 };
 
 struct SparseWarpSolver {
@@ -156,6 +157,7 @@ struct SparseWarpSolver {
         st.rent = st.rcol + nnz;
         st.lmap = st.rent + nnz;
         in.fcap = fcap;
+        in.windowed = M.sp.windowed;
         in.sv = w.J.p;
         in.tval = w.A.p; // pivot-row scratch of a factorisation (aliases x_new unless the vectors live in global memory)
         u16 *hb = reinterpret_cast<u16 *>(w.piv.p);
@@ -218,6 +220,169 @@ struct SparseWarpSolver {
         e = __shfl_sync(0xffffffffu, e, src);
     }
 
+    // Up to 32 consecutive elimination steps at once.  Lane l examines column k0 + l on the matrix as it stands: pivot
+    // search, multipliers, the entries its updates would touch.  That is the sequential algorithm's view of the
+    // column if (a) every earlier column of the window pivots on the row already sitting at its position (no swap:
+    // positions stay as they are) and (b) no earlier pivot row of the window holds an entry in this column (then no
+    // update of the window writes into it).  The window is cut at the first column for which that cannot be shown —
+    // or that needs a swap, fill-in, more than two targets / pivot-row entries, or meets a zero / non-finite
+    // candidate — and what is left is applied in column order by one lane, so that every sum is accumulated in the
+    // sequential order (the rail column of an inverter chain is a true recurrence).  Returns the columns done.
+    static __device__ __forceinline__ int window(const Team &tm, const SpStatic &st, const SpInst &in, double *__restrict__ y,
+                                                 int k0, unsigned long long &flops)
+    {
+        const int n = st.n, nnz = st.nnz, lane = tm.rank;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        const int nw = min(32, n - k0), k = k0 + lane;
+        bool valid = lane < nw;
+        int P = -1, eP = -1, nt = 0, npv = 0;
+        int tr[2] = {0, 0}, te[2] = {0, 0}, pe2[2] = {0, 0}, pj[2] = {0, 0}, e2[4] = {0, 0, 0, 0};
+        double tmul[2] = {0.0, 0.0};
+        bool tnz[2] = {false, false};
+        unsigned dirty = 0;
+        int c0 = 0, c1 = 0;
+        if (valid) {
+            c0 = st.cptr[k];
+            c1 = st.cptr[k + 1];
+            double bv = -1.0;
+            int bp = 0x7fffffff;
+            bool bad = false;
+            for (int t = c0; t < c1; ++t) {
+                const int r = st.erow[t], p = in.pos[r];
+                if (p >= k) {
+                    const double v = fabs(in.sv[t]);
+                    bad |= !(v < INF);
+                    if (v > bv || (v == bv && p < bp)) {
+                        bv = v;
+                        bp = p;
+                        P = r;
+                        eP = t;
+                    }
+                }
+            }
+            for (u16 f = in.chead[k]; f != SP_NONE; f = in.fnc[f]) {
+                const int r = in.fr[f], p = in.pos[r];
+                if (p >= k) {
+                    const double v = fabs(in.sv[nnz + f]);
+                    bad |= !(v < INF);
+                    if (v > bv || (v == bv && p < bp)) {
+                        bv = v;
+                        bp = p;
+                        P = r;
+                        eP = nnz + (int)f;
+                    }
+                }
+            }
+            valid = !bad && bv > 0.0 && bp == k; // the pivot sits at its position already
+        }
+        if (valid) { // pivot row: entries with column > k
+            for (int t = st.rptr[P]; t < st.rptr[P + 1]; ++t) {
+                const int j = st.rcol[t];
+                if (j > k) {
+                    if (npv < 2) {
+                        pj[npv] = j;
+                        pe2[npv] = st.rent[t];
+                    }
+                    ++npv;
+                    if (j < k0 + nw) dirty |= 1u << (j - k0);
+                }
+            }
+            for (u16 f = in.rhead[P]; f != SP_NONE; f = in.fnr[f]) {
+                const int j = in.fc[f];
+                if (j > k) {
+                    if (npv < 2) {
+                        pj[npv] = j;
+                        pe2[npv] = nnz + (int)f;
+                    }
+                    ++npv;
+                    if (j < k0 + nw) dirty |= 1u << (j - k0);
+                }
+            }
+            valid = npv <= 2;
+        }
+        if (valid) { // rows below: multipliers and the entries their updates touch
+            const double alpha = 1.0 / in.sv[eP]; // (:31)
+            for (int t = c0; t < c1; ++t) {
+                const int r = st.erow[t];
+                if ((int)in.pos[r] > k) {
+                    if (nt < 2) {
+                        const double a = in.sv[t];
+                        tr[nt] = r;
+                        te[nt] = t;
+                        tmul[nt] = alpha * a;
+                        tnz[nt] = a != 0.0;
+                    }
+                    ++nt;
+                }
+            }
+            for (u16 f = in.chead[k]; f != SP_NONE; f = in.fnc[f]) {
+                const int r = in.fr[f];
+                if ((int)in.pos[r] > k) {
+                    if (nt < 2) {
+                        const double a = in.sv[nnz + f];
+                        tr[nt] = r;
+                        te[nt] = nnz + (int)f;
+                        tmul[nt] = alpha * a;
+                        tnz[nt] = a != 0.0;
+                    }
+                    ++nt;
+                }
+            }
+            valid = nt <= 2;
+            if (valid) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (t < nt && tnz[t] && q < npv) {
+                            const int e = lookup(st, in, tr[t], pj[q]);
+                            e2[t * 2 + q] = e;
+                            valid = valid && e >= 0; // a missing entry would be fill-in: the sequential step creates it
+                        }
+            }
+        }
+        // extent of the window
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        int ext = __ffs((int)~vmask) - 1; // first lane that is not valid (32 if none)
+        if (ext < 0) ext = 32;
+        ext = min(ext, nw);
+        const unsigned dm = __reduce_or_sync(0xffffffffu, lane < ext ? dirty : 0u);
+        if (dm) ext = min(ext, __ffs((int)dm) - 1);
+        if (ext <= 0) return 0;
+        // multipliers (every lane its own column's entries)
+        if (lane < ext) {
+            in.pe[k] = (u16)eP;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (t < nt) in.sv[te[t]] = tmul[t];
+        }
+        __syncwarp();
+        // the updates, in column order; lane 0 does the arithmetic, the owners supply the operands
+        for (int c = 0; c < ext; ++c) {
+            const int Pc = __shfl_sync(0xffffffffu, P, c);
+            const int ntc = __shfl_sync(0xffffffffu, nt, c), npc = __shfl_sync(0xffffffffu, npv, c);
+            const double yk = y[Pc];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int r = __shfl_sync(0xffffffffu, tr[t], c);
+                const double m = __shfl_sync(0xffffffffu, tmul[t], c);
+                const int nz = __shfl_sync(0xffffffffu, (int)tnz[t], c);
+                if (t < ntc && nz) {
+                    flops += 3 + 2 * npc;
+                    if (lane == 0) y[r] = y[r] - m * yk; // (:40)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int ed = __shfl_sync(0xffffffffu, e2[t * 2 + q], c);
+                        const int es = __shfl_sync(0xffffffffu, pe2[q], c);
+                        if (q < npc && lane == 0) in.sv[ed] = in.sv[ed] - m * in.sv[es]; // (:35-39)
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        return ext;
+    }
+
     // gauss_lu.rs:3-42 on the sparse storage, rhs y carried along.  Returns false -> abandon the instance (ST_REDO).
     // (0 = ok, 1 = zero / non-finite pivot candidate, 2 = fill-in pool exhausted)
     // flops: executed floating-point operations; nfill_out: fill-in entries created
@@ -236,6 +401,13 @@ struct SparseWarpSolver {
         int nfill = 0;
         __syncwarp();
         for (int k = 0; k < n; ++k) {
+            if (in.windowed) { // as many independent columns as can be shown independent, at once
+                const int done = window(tm, st, in, y, k, flops);
+                if (done > 0) {
+                    k += done - 1;
+                    continue;
+                }
+            }
             const int c0 = st.cptr[k], c1 = st.cptr[k + 1];
             // ---- pivot search over the entries of column k held by rows at positions >= k ----
             double bv = -1.0;

@@ -405,6 +405,11 @@ def test_mid_size_kernels_agree_bitwise(which):
     B = 5
     vals, fns = nl.monte_carlo(circ, B)
     v_sp, c_sp, o_sp = _run_mid(circ, vals, fns, {})
+    for forced in (0, 2):  # windowed elimination off / forced on (the default decides from the predicted structure)
+        _, c_f, o_f = _run_mid(circ, vals, fns, {"windowed": forced, "slots_global": forced // 2})
+        assert c_f["redo"] == 0
+        for a, b in zip(o_sp, o_f):
+            assert np.array_equal(a, b, equal_nan=True)
     v_w, _, o_w = _run_mid(circ, vals, fns, {"sparse_warp": 0})
     v_g, _, o_g = _run_mid(circ, vals, fns, {"force_generic": 1})
     assert v_sp.startswith("spw_n"), v_sp
