@@ -590,6 +590,68 @@ struct SparseWarpSolver {
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         bool ok = true;
         for (int i = n - 1; i >= 0; --i) {
+            if (in.windowed) {
+                // Window of up to 32 columns (descending).  Lane l takes column i - l: its solution component is
+                // y[row] / pivot as soon as no later column of the window holds an entry in its pivot row (then nothing
+                // the window does writes into that y).  All divisions of the window run in parallel; the few columns
+                // that hold entries of U are then applied in descending order, as the sequential loop would.
+                const int nw = min(32, i + 1), ic = i - lane;
+                bool valid = lane < nw;
+                int ri = 0, nU = 0;
+                if (valid) {
+                    ri = in.piv[ic];
+                    for (int t = st.rptr[ri]; t < st.rptr[ri + 1] && valid; ++t) {
+                        const int j = st.rcol[t];
+                        if (j > ic && j <= i) valid = false;
+                    }
+                    for (u16 f = in.rhead[ri]; f != SP_NONE && valid; f = in.fnr[f]) {
+                        const int j = in.fc[f];
+                        if (j > ic && j <= i) valid = false;
+                    }
+                    for (int t = st.cptr[ic]; t < st.cptr[ic + 1]; ++t) nU += (int)in.pos[st.erow[t]] < ic ? 1 : 0;
+                    for (u16 f = in.chead[ic]; f != SP_NONE; f = in.fnc[f]) nU += (int)in.pos[in.fr[f]] < ic ? 1 : 0;
+                }
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                int ext = __ffs((int)~vmask) - 1;
+                if (ext < 0) ext = 32;
+                ext = min(ext, nw);
+                if (ext >= 2) {
+                    // a column with entries of U changes y of rows that later lanes of the window read only if that
+                    // row is one of their pivot rows: excluded above for entries INSIDE the window; a U entry of
+                    // column ic sits in a row pivoted before ic, i.e. the pivot row of a LATER lane -> cut there too
+                    unsigned ucols = __ballot_sync(0xffffffffu, lane < ext && nU > 0);
+                    // rows touched by column ic's U entries have positions < ic: lanes > l.  Keep only the first such
+                    // column and end the window right after it.
+                    if (ucols) ext = min(ext, __ffs((int)ucols));
+                    double xi = 0.0;
+                    if (lane < ext) {
+                        xi = y[ri] / in.sv[in.pe[ic]];
+                        xp[ic] = xi;
+                    }
+                    ok = ok && __all_sync(0xffffffffu, lane >= ext || fabs(xi) < INF);
+                    __syncwarp();
+                    ucols &= ext >= 32 ? 0xffffffffu : ((1u << ext) - 1u);
+                    if (ucols) { // at most one: the last column of the window
+                        const int l = __ffs((int)ucols) - 1, iu = i - l;
+                        const double xu = __shfl_sync(0xffffffffu, xi, l);
+                        const int c0 = st.cptr[iu], c1 = st.cptr[iu + 1];
+                        for (int t = c0 + lane; t < c1; t += 32) {
+                            const int r = st.erow[t];
+                            if ((int)in.pos[r] < iu) y[r] = y[r] - xu * in.sv[t];
+                        }
+                        int q = 0;
+                        for (u16 f = in.chead[iu]; f != SP_NONE; f = in.fnc[f], ++q) {
+                            if ((q & 31) == lane) {
+                                const int r = in.fr[f];
+                                if ((int)in.pos[r] < iu) y[r] = y[r] - xu * in.sv[nnz + f];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    i -= ext - 1;
+                    continue;
+                }
+            }
             const int ri = in.piv[i];
             const double xi = y[ri] / in.sv[in.pe[i]];
             ok = ok && (fabs(xi) < INF);
