@@ -383,7 +383,8 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     if (n >= 0xfff0) return 1; // u16 indices
     if (nnz + fcap >= 0xfff0) fcap = (0xfff0 - nnz - 2) & ~1;
     if (fcap < 2) return 1;
-    KernelFn fn = sparse_kernel(an);
+    const bool win = c->windowed == 2 || (c->windowed == 1 && mo.sp.window_hint >= 4);
+    KernelFn fn = sparse_kernel(an, win);
     const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
     SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
     if (T.bytes > 32 * 1024) { // large circuit: per-step history (and optionally the slot table) to global scratch

@@ -126,7 +126,9 @@ struct SpInst {
     int windowed; // try to eliminate windows of independent columns at once
 };
 
-struct SparseWarpSolver {
+// WIN: compile the windowed elimination / back substitution in (separate kernels: the extra code costs registers)
+template <bool WIN>
+struct SparseWarpSolverT {
     using Team = WarpTeam;
     static constexpr bool kHasA = false;
     static constexpr bool kHasB = false;
@@ -401,7 +403,7 @@ struct SparseWarpSolver {
         int nfill = 0;
         __syncwarp();
         for (int k = 0; k < n; ++k) {
-            if (in.windowed) { // as many independent columns as can be shown independent, at once
+            if (WIN && in.windowed) { // as many independent columns as can be shown independent, at once
                 const int done = window(tm, st, in, y, k, flops);
                 if (done > 0) {
                     k += done - 1;
@@ -590,7 +592,7 @@ struct SparseWarpSolver {
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         bool ok = true;
         for (int i = n - 1; i >= 0; --i) {
-            if (in.windowed) {
+            if (WIN && in.windowed) {
                 // Window of up to 32 columns (descending).  Lane l takes column i - l: its solution component is
                 // y[row] / pivot as soon as no later column of the window holds an entry in its pivot row (then nothing
                 // the window does writes into that y).  All divisions of the window run in parallel; the few columns
@@ -827,7 +829,7 @@ struct SparseWarpSolver {
 };
 
 // one warp per instance; the warps of a block share the u16 copy of the static structure
-template <int AN>
+template <int AN, bool WIN>
 __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -886,7 +888,7 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
         inst = __shfl_sync(0xffffffffu, inst, 0);
         if (inst < 0) break;
         Counters ci;
-        run_instance<WarpTeam, SparseWarpSolver, AN>(tm, a, w, inst, ci);
+        run_instance<WarpTeam, SparseWarpSolverT<WIN>, AN>(tm, a, w, inst, ci);
         tm.sync();
         int st = 0;
         if (tm.rank == 0) st = a.status[inst];
@@ -905,6 +907,6 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     flush_counters(tm, a, cn);
 }
 
-KernelFn sparse_kernel(int an); // kern_sparse.cu
+KernelFn sparse_kernel(int an, bool windowed); // kern_sparse.cu
 
 } // namespace ftsb
