@@ -384,7 +384,6 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     if (nnz + fcap >= 0xfff0) fcap = (0xfff0 - nnz - 2) & ~1;
     if (fcap < 2) return 1;
     const bool win = c->windowed == 2 || (c->windowed == 1 && mo.sp.window_hint >= 4);
-    KernelFn fn = sparse_kernel(an, win);
     const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
     SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
     if (T.bytes > 32 * 1024) { // large circuit: per-step history (and optionally the slot table) to global scratch
@@ -397,6 +396,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
         fcap = (fcap / 2 + 1) & ~1;
         T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global);
     }
+    KernelFn fn = sparse_kernel(an, win, hist_global != 0);
     const size_t per_warp = (T.bytes + 15) & ~(size_t)15;
     int best_w = 0, best_occ = 0;
     size_t best_smem = 0;

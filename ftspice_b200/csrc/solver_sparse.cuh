@@ -829,7 +829,9 @@ struct SparseWarpSolverT {
 };
 
 // one warp per instance; the warps of a block share the u16 copy of the static structure
-template <int AN, bool WIN>
+// GLOB: slot table / solution vectors / history may live in global scratch (large circuits); without it every working-
+// set pointer is provably shared memory and the compiler emits LDS / STS instead of generic accesses
+template <int AN, bool WIN, bool GLOB>
 __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -866,16 +868,26 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     {
         // per-step history (C/L state, last three accepted x): shared memory, or — large circuits — a global
         // scratch row per resident warp (touched once per accepted step, coalesced)
-        double *gb = a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles;
-        const bool hist_g = AN == AN_TRAN && (M.sp.hist_global & 1);
-        w.state.p = (hist_g ? gb : base) + T.ostate;
-        w.ring.p = (hist_g ? gb : base) + T.oring;
-        w.val.p = (T.val_global ? gb : base) + T.oval; // large slot tables: L2-resident scratch (more warps per SM)
-        double *vb = T.vec_global ? gb : base;
-        w.x.p = vb + T.ox;
-        w.xn.p = vb + T.oxn;
-        w.xp.p = vb + T.oxp;
-        w.b.p = vb + T.obv;
+        if constexpr (GLOB) {
+            double *gb = a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles;
+            const bool hist_g = AN == AN_TRAN && (M.sp.hist_global & 1);
+            w.state.p = (hist_g ? gb : base) + T.ostate;
+            w.ring.p = (hist_g ? gb : base) + T.oring;
+            w.val.p = (T.val_global ? gb : base) + T.oval; // large slot tables: L2-resident scratch (more warps per SM)
+            double *vb = T.vec_global ? gb : base;
+            w.x.p = vb + T.ox;
+            w.xn.p = vb + T.oxn;
+            w.xp.p = vb + T.oxp;
+            w.b.p = vb + T.obv;
+        } else {
+            w.state.p = base + T.ostate;
+            w.ring.p = base + T.oring;
+            w.val.p = base + T.oval;
+            w.x.p = base + T.ox;
+            w.xn.p = base + T.oxn;
+            w.xp.p = base + T.oxp;
+            w.b.p = base + T.obv;
+        }
         w.A.p = base + T.otval; // (the dense A is not kept by this solver: the field carries the pivot-row scratch)
     }
     w.piv.p = reinterpret_cast<int *>(base + T.doubles);
@@ -907,6 +919,6 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     flush_counters(tm, a, cn);
 }
 
-KernelFn sparse_kernel(int an, bool windowed); // kern_sparse.cu
+KernelFn sparse_kernel(int an, bool windowed, bool global_scratch); // kern_sparse.cu
 
 } // namespace ftsb

@@ -706,3 +706,23 @@ def test_plan_kernel_equals_dense_kernel_bitwise_dc(jit, oracle_mod):
         assert np.array_equal(a, b, equal_nan=True)
     st, done, it, x = oracle_mod.Oracle(circ).batch_dc(vals, None, se, start, stop, step, Lp, threads=8)
     assert (outs[0][1][0] == st).all() and (outs[0][1][1] == done).all()
+
+
+def test_sparse_kernel_c5_through_the_input_edge(oracle_mod):
+    """C5 topology (256-node inverter chain, n = 258) through the rising edge of the input pulse (1 ns .. 3 ns): many
+    Newton iterations per step, Newton-failure retries, instances that stop with the reference's error.  Status,
+    record counts, iteration counts and time stamps equal the oracle's; unknowns within tolerance."""
+    circ = nl.load(nl.inverter_chain_netlist(256, stop="3.2n", step="50p"))
+    B = 4
+    vals, fns = nl.monte_carlo(circ, B)
+    t = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    r = be.run_tran(t.stop, t.step, capacity=200, rec_stride=1)
+    assert be.variant.startswith("spw_n258")
+    st, nrec, it, tt, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals, fns, t.stop, t.step, 200, threads=4)
+    assert (r.status == st).all() and (r.n_rec == nrec).all(), (r.status, st, r.n_rec, nrec)
+    for i in range(B):
+        k = min(int(nrec[i]), 200)
+        assert (r.t[i, :k] == tt[i, :k]).all() and (r.n_iters[i, :k] == it[i, :k]).all()
+        assert_close(r.x[i, :k], x[i, :k], f"C5 instance {i}")
