@@ -726,3 +726,75 @@ def test_sparse_kernel_c5_through_the_input_edge(oracle_mod):
         k = min(int(nrec[i]), 200)
         assert (r.t[i, :k] == tt[i, :k]).all() and (r.n_iters[i, :k] == it[i, :k]).all()
         assert_close(r.x[i, :k], x[i, :k], f"C5 instance {i}")
+
+
+def _random_netlist(rng, n_nodes):
+    """A random connected small circuit: a resistor spanning tree, extra R / I / D / Q / M elements, two V sources (one
+    with a waveform, evaluated at t = 0 by .op / .dc)."""
+    nodes = [str(i) for i in range(1, n_nodes + 1)]
+    lines = ["* random circuit"]
+    k = 0
+
+    def name(prefix):
+        nonlocal k
+        k += 1
+        return f"{prefix}{k}"
+
+    lines.append(f"{name('V')} {nodes[0]} 0 {rng.integers(1, 6)}V")
+    lines.append(f"{name('V')} {nodes[1]} 0 SIN( {rng.integers(1, 4)} 1.0 10M )")
+    for i in range(1, n_nodes):  # spanning tree
+        j = int(rng.integers(0, i))
+        lines.append(f"{name('R')} {nodes[i]} {nodes[j]} R={int(rng.integers(1, 50)) * 100}")
+    for i in range(n_nodes):
+        if rng.random() < 0.5:
+            lines.append(f"{name('R')} {nodes[i]} 0 R={int(rng.integers(1, 20))}k")
+    for _ in range(int(rng.integers(1, 4))):
+        a, b, c = (nodes[int(x)] for x in rng.choice(n_nodes, 3, replace=False))
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            lines.append(f"{name('D')} {'0' if rng.random() < 0.5 else a} {b} d_model")
+        elif kind == 1:
+            lines.append(f"{name('Q')} {a} {b} {'0' if rng.random() < 0.5 else c} 0 q_model")
+        elif kind == 2:
+            lines.append(f"{name('M')} {a} {b} {'0' if rng.random() < 0.6 else c} 0 t_model")
+        else:
+            lines.append(f"{name('I')} {a} {'0' if rng.random() < 0.5 else b} {int(rng.integers(1, 9))}mA")
+    lines += [".OP", ".END", ""]
+    return "\n".join(lines)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_jit_kernel_random_circuits(seed, oracle_mod):
+    """Generated per-topology kernels on random small circuits (3..12 nodes): bitwise equal to the dense kernel, and
+    equal to the oracle in status / iteration counts / values for .op and for a .dc sweep of the first source."""
+    rng = np.random.default_rng(1000 + seed)
+    circ = nl.load(_random_netlist(rng, int(rng.integers(3, 13))))
+    B = 300
+    vals, fns = nl.monte_carlo(circ, B, rel=0.2)
+    outs = {}
+    for mode, opts in (("jit", {}), ("dense", {"plan": 0})):
+        be = BatchEngine(circ)
+        for k, v in opts.items():
+            be.set_option(k, v)
+        be.set_params(vals, fns)
+        r = be.run_op()
+        d = be.run_dc(0, 0.0, 2.0, 0.25)
+        outs[mode] = (be.variant, (r.status, r.n_iters, r.x, d.status, d.points_done, d.n_iters, d.x))
+    assert outs["jit"][0].startswith(("jit", "plan", "sync")), outs["jit"][0]
+    for a, b in zip(outs["jit"][1], outs["dense"][1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    orc_ = oracle_mod.Oracle(circ)
+    st, it, x = orc_.batch_op(vals, fns, threads=8)
+    r_status, r_it, r_x = outs["jit"][1][:3]
+    assert (r_status == st).all()
+    ok = st == 0
+    assert (r_it[ok] == it[ok]).all()
+    if ok.any():
+        assert_close(r_x[ok], x[ok], f"random circuit {seed} .op")
+    ones = np.ones(B)
+    dst, done, dit, dx = orc_.batch_dc(vals, fns, 0, 0.0 * ones, 2.0 * ones, 0.25 * ones, 8, threads=8)
+    assert (outs["jit"][1][3] == dst).all() and (outs["jit"][1][4] == done).all()
+    for i in range(0, B, 7):
+        kk = int(done[i])
+        assert (outs["jit"][1][5][i, :kk] == dit[i, :kk]).all()
+        assert_close(outs["jit"][1][6][i, :kk], dx[i, :kk], f"random circuit {seed} .dc chain {i}")
