@@ -90,6 +90,7 @@ struct ftsb_circuit {
     int force_generic = 0; // 1: never use the small-circuit lane kernels (A/B testing)
     int lanes = 0;         // >0: lanes per instance requested for the dense small-circuit kernels (if built)
     int sparse_warp = 1;   // 1 (default): structure-exploiting warp-per-instance kernels for n > 16
+    int hist_global_opt = 0; // 1: mid-size .tran keeps the per-step history in global scratch (no gain at n = 65: registers bound the occupancy)
     int windowed = 1;      // 1: the sparse kernel eliminates windows of independent columns at once when the predicted
                            // structure allows it; 2: always try; 0: never
     int slots_global = 1;  // 1: large circuits keep the slot table and the solution vectors in L2-resident global scratch
@@ -386,6 +387,11 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
     const bool win = c->windowed == 2 || (c->windowed == 1 && mo.sp.window_hint >= 4);
     const size_t stat = sp_static_bytes(n, nnz, mo.sp.n_long);
     SpLayout T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN);
+    if (an == AN_TRAN && c->hist_global_opt && T.bytes <= 32 * 1024 && T.bytes > 6 * 1024) {
+        // mid-size .tran: the per-step history (touched once per accepted step) to global scratch: more warps per SM
+        hist_global = 1;
+        T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, true, hist_global);
+    }
     if (T.bytes > 32 * 1024) { // large circuit: per-step history (and optionally the slot table) to global scratch
         // 1: per-step history, 2: slot table, 4: x / x_new / x_proposed / b -> L2-resident global scratch; what stays in
         // shared memory is what the sequential elimination touches (matrix entries, rhs, structure)
@@ -396,7 +402,7 @@ int plan_sparse(ftsb_circuit *c, int an, long long batch, LaunchPlan &pl, int &f
         fcap = (fcap / 2 + 1) & ~1;
         T = sp_layout(n, nnz, fcap, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, an == AN_TRAN, hist_global);
     }
-    KernelFn fn = sparse_kernel(an, win, hist_global != 0);
+    KernelFn fn = sparse_kernel(an, win, (hist_global & 6) ? 2 : (hist_global & 1) ? 1 : 0);
     const size_t per_warp = (T.bytes + 15) & ~(size_t)15;
     int best_w = 0, best_occ = 0;
     size_t best_smem = 0;
@@ -917,6 +923,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->jit_min_blocks = (int)value;
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "hist_global"))
+        c->hist_global_opt = value ? 1 : 0;
     else if (!strcmp(name, "windowed"))
         c->windowed = (int)value;
     else if (!strcmp(name, "slots_global"))

@@ -2,14 +2,16 @@
 #include "solver_sparse.cuh"
 
 namespace ftsb {
-template <bool WIN, bool GLOB>
+template <bool WIN, int GLOB>
 static KernelFn pick(int an)
 {
     return an == AN_OP ? (KernelFn)k_spw<AN_OP, WIN, GLOB> : an == AN_DC ? (KernelFn)k_spw<AN_DC, WIN, GLOB> : (KernelFn)k_spw<AN_TRAN, WIN, GLOB>;
 }
-KernelFn sparse_kernel(int an, bool windowed, bool global_scratch)
+// global_scratch: 0 = none, 1 = per-step history only (.tran), 2 = history + slot table + vectors
+KernelFn sparse_kernel(int an, bool windowed, int global_scratch)
 {
-    if (global_scratch) return windowed ? pick<true, true>(an) : pick<false, true>(an);
-    return windowed ? pick<true, false>(an) : pick<false, false>(an);
+    if (global_scratch == 2) return windowed ? pick<true, 2>(an) : pick<false, 2>(an);
+    if (global_scratch == 1 && an == AN_TRAN) return windowed ? pick<true, 1>(an) : pick<false, 1>(an);
+    return windowed ? pick<true, 0>(an) : pick<false, 0>(an);
 }
 } // namespace ftsb

@@ -829,9 +829,10 @@ struct SparseWarpSolverT {
 };
 
 // one warp per instance; the warps of a block share the u16 copy of the static structure
-// GLOB: slot table / solution vectors / history may live in global scratch (large circuits); without it every working-
-// set pointer is provably shared memory and the compiler emits LDS / STS instead of generic accesses
-template <int AN, bool WIN, bool GLOB>
+// GLOB: 0 = the whole working set is in shared memory (every pointer provably shared: LDS / STS, no generic accesses);
+// 1 = the per-step history (C/L state, ring of accepted x) lives in global scratch; 2 = so may the slot table and the
+// solution vectors (large circuits)
+template <int AN, bool WIN, int GLOB>
 __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -868,7 +869,16 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     {
         // per-step history (C/L state, last three accepted x): shared memory, or — large circuits — a global
         // scratch row per resident warp (touched once per accepted step, coalesced)
-        if constexpr (GLOB) {
+        if constexpr (GLOB == 1) {
+            double *gb = a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles;
+            w.state.p = gb + T.ostate;
+            w.ring.p = gb + T.oring;
+            w.val.p = base + T.oval;
+            w.x.p = base + T.ox;
+            w.xn.p = base + T.oxn;
+            w.xp.p = base + T.oxp;
+            w.b.p = base + T.obv;
+        } else if constexpr (GLOB == 2) {
             double *gb = a.scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T.hist_doubles;
             const bool hist_g = AN == AN_TRAN && (M.sp.hist_global & 1);
             w.state.p = (hist_g ? gb : base) + T.ostate;
@@ -919,6 +929,6 @@ __global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
     flush_counters(tm, a, cn);
 }
 
-KernelFn sparse_kernel(int an, bool windowed, bool global_scratch); // kern_sparse.cu
+KernelFn sparse_kernel(int an, bool windowed, int global_scratch); // kern_sparse.cu
 
 } // namespace ftsb
