@@ -832,11 +832,10 @@ struct SparseWarpSolverT {
 // GLOB: 0 = the whole working set is in shared memory (every pointer provably shared: LDS / STS, no generic accesses);
 // 1 = the per-step history (C/L state, ring of accepted x) lives in global scratch; 2 = so may the slot table and the
 // solution vectors (large circuits)
-#ifndef SPW_MIN_BLOCKS
-#define SPW_MIN_BLOCKS 1
-#endif
 template <int AN, bool WIN, int GLOB>
-__global__ void __launch_bounds__(128, SPW_MIN_BLOCKS) k_spw(const __grid_constant__ RunArgs a)
+// (no min-blocks argument: nvcc then settles on 128 registers, 16 warps per SM at n = 65; asking for 1 block gives 174
+// registers / 8 warps and 5 blocks gives 96 registers with more spills — both measured slower)
+__global__ void __launch_bounds__(128) k_spw(const __grid_constant__ RunArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevProg &P = a.prog;
