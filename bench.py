@@ -301,8 +301,8 @@ def main():
         elif wl["kind"] == "dc":
             P = wl["points"]
             d_start, d_stop, d_step = (torch.from_numpy(a).to(dev) for a in (start, stop, stp))
-            d_x = torch.empty((B, P, n_out), dtype=torch.float64, device=dev)
-            d_it = torch.empty((B, P), dtype=torch.int32, device=dev)
+            d_x = torch.zeros((B, P, n_out), dtype=torch.float64, device=dev)
+            d_it = torch.zeros((B, P), dtype=torch.int32, device=dev)
             d_done = torch.empty(B, dtype=torch.int64, device=dev)
         else:
             d_x = torch.empty((B, n_out), dtype=torch.float64, device=dev)  # x_final only: full waveforms of the
@@ -339,14 +339,17 @@ def main():
     L = capi.lib()
 
     def step_host():
-        capi.check(L.ftsb_set_params(be.h, B, vp(h_vals), vp(h_fns) if be.n_fn else None, capi.LAYOUT_INSTANCE_MAJOR,
-                                     capi.MEM_HOST), be.h)
+        # the call a user makes with host buffers: parameters in, results out, blocking (ftsb_solve_op / ftsb_solve_dc
+        # cut the batch into chunks so that the copies of one chunk overlap the solve of the others)
+        fnp = vp(h_fns) if be.n_fn else None
         if wl["kind"] == "op":
-            capi.check(L.ftsb_run_op(be.h, vp(ho_x), vp(ho_it), vp(ho_st), capi.MEM_HOST), be.h)
+            capi.check(L.ftsb_solve_op(be.h, B, vp(h_vals), fnp, capi.LAYOUT_INSTANCE_MAJOR, vp(ho_x), vp(ho_it), vp(ho_st)), be.h)
         elif wl["kind"] == "dc":
-            capi.check(L.ftsb_run_dc(be.h, circ.elem_index(wl["sweep"]), vp(h_rng[0]), vp(h_rng[1]), vp(h_rng[2]), P,
-                                     vp(ho_x), vp(ho_it), vp(ho_done), vp(ho_st), capi.MEM_HOST), be.h)
+            capi.check(L.ftsb_solve_dc(be.h, B, vp(h_vals), fnp, capi.LAYOUT_INSTANCE_MAJOR, circ.elem_index(wl["sweep"]),
+                                       vp(h_rng[0]), vp(h_rng[1]), vp(h_rng[2]), P, vp(ho_x), vp(ho_it), vp(ho_done),
+                                       vp(ho_st)), be.h)
         else:
+            capi.check(L.ftsb_set_params(be.h, B, vp(h_vals), fnp, capi.LAYOUT_INSTANCE_MAJOR, capi.MEM_HOST), be.h)
             opts = capi.FtsbTranOpts(0, 1, 0)
             capi.check(L.ftsb_run_tran(be.h, wl["stop"], wl["step"], ct.byref(opts), None, None, None, vp(ho_nrec),
                                        vp(ho_x), vp(ho_st), capi.MEM_HOST), be.h)
@@ -390,11 +393,16 @@ def main():
     t_wall0 = time.perf_counter()
     ms_dev = timed(step_device, args.steps)
     launches = be.launch_count - launches0
+    dev_variant = be.variant
     barrier()
     t_wall = time.perf_counter() - t_wall0
     cnt = be.counters()
     ms_e2e = timed(step_host, args.steps)
     barrier()
+    e2e_variant = be.variant
+    # the host-buffer path must have produced what the device path produced (same instances, same kernel arithmetic)
+    if not (torch.equal(ho_x.view(torch.int64), d_x.cpu().view(torch.int64)) and torch.equal(ho_st, d_st.cpu())):
+        raise RuntimeError("bench: host-buffer (e2e) results differ from the device-buffer results")
     clocks = sampler.stop() if rank == 0 else {}
 
     # solve points of one step on this rank (device results of the last device step)
@@ -429,13 +437,13 @@ def main():
         e2e_v = pts_all * args.steps / (e2e_ms_total * 1e-3)
         fm = flop_model(circ, wl["kind"] if wl["kind"] == "op" else "run")
         ref_flops = cnt["newton_iters"] * (fm["factor"] + fm["solve"] + fm["rest"])
-        sparse = be.variant.startswith(("spw", "jit", "plan"))  # kernels that skip structural zeros: device / plan flop counts
+        sparse = dev_variant.startswith(("spw", "jit", "plan"))  # kernels that skip structural zeros: device / plan flop counts
         if sparse:  # structure-exploiting kernel: flops it actually executed (device counter) + the per-iteration rest
             exec_flops = cnt["sparse_flops"] + cnt["newton_iters"] * fm["rest_exec"]
         else:
             exec_flops = cnt["lu_factor"] * fm["factor"] + cnt["lu_solve"] * fm["solve"] + cnt["newton_iters"] * fm["rest_exec"]
         kern_ms = float(np.mean(ms_dev))  # events bracket the step's launches (one kernel for .op/.dc; start-up + run for .tran)
-        v0 = be.variant.split("/")[0]
+        v0 = dev_variant.split("/")[0]
         kname = ("ftsb_jit (NVRTC, per topology)" if v0.startswith("jit") else "k_plan" if v0.startswith("plan") else
                  "k_spw" if v0.startswith("spw") else "k_sync" if v0.startswith(("sync", "zskip")) else
                  "k_lanes" if v0.startswith("lanes") else "k_warp" if "r_n" in v0 else
@@ -445,7 +453,7 @@ def main():
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             ent = tj.get(args.workload, {})
-            if ent.get("variant_prefix") and be.variant.startswith(ent["variant_prefix"]) and args.scale == 1.0:
+            if ent.get("variant_prefix") and dev_variant.startswith(ent["variant_prefix"]) and args.scale == 1.0:
                 traffic = ent["dram_bytes_per_launch"]
                 ncu_extra = {k: ent[k] for k in ("fp64_pipe_pct", "issue_active_pct", "warp_instructions_per_launch") if k in ent}
         except Exception:
@@ -465,17 +473,17 @@ def main():
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if wl["kind"] != "dc" else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["label"], "instances_per_gpu": B, "n_unknowns": fm["n"], "variant": be.variant,
+            "config": {"workload": wl["label"], "instances_per_gpu": B, "n_unknowns": fm["n"], "variant": dev_variant,
                        "l2": "flushed (256 MiB memset) between timed steps", "converged_instances": int(ok_all),
                        "solve_points_per_step": int(pts_all), "arithmetic": "fp64, no FMA contraction on the solution path",
                        "wall_s_timed_region": t_wall, "final_gather_ms_untimed": gather_ms},
             "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms_total / args.steps},
+                    "ms_per_step": e2e_ms_total / args.steps, "variant": e2e_variant},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
-                         "kernel": f"{kname}<{wl['kind']}> ({be.variant})",
+                         "kernel": f"{kname}<{wl['kind']}> ({dev_variant})",
                          "kernel_ms": kern_ms, "executed_flops_per_launch": exec_flops,
                          "reference_equivalent_flops_per_launch": ref_flops,
                          "peak_source": "DFMA micro-benchmark in this run (ftsb_measure_fp64_tflops); MEASURED_PEAKS.json has no "

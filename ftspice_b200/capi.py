@@ -23,7 +23,7 @@ EXPORTS = [
     "ftsb_abi_version", "ftsb_device_count", "ftsb_last_error", "ftsb_compile", "ftsb_destroy", "ftsb_n_elems",
     "ftsb_n_run", "ftsb_n_start", "ftsb_n_fn", "ftsb_set_option", "ftsb_set_params", "ftsb_run_op", "ftsb_run_dc",
     "ftsb_run_tran", "ftsb_sync", "ftsb_stream", "ftsb_set_stream", "ftsb_get_counters", "ftsb_launch_count",
-    "ftsb_last_variant", "ftsb_lu_solve", "ftsb_measure_fp64_tflops",
+    "ftsb_last_variant", "ftsb_lu_solve", "ftsb_measure_fp64_tflops", "ftsb_solve_op", "ftsb_solve_dc",
 ]
 
 
@@ -87,6 +87,10 @@ def lib() -> ct.CDLL:
     L.ftsb_run_op.restype = ct.c_int
     L.ftsb_run_dc.argtypes = [vp, i32, vp, vp, vp, i64, vp, vp, vp, vp, ct.c_int]
     L.ftsb_run_dc.restype = ct.c_int
+    L.ftsb_solve_op.argtypes = [vp, i64, vp, vp, ct.c_int, vp, vp, vp]
+    L.ftsb_solve_op.restype = ct.c_int
+    L.ftsb_solve_dc.argtypes = [vp, i64, vp, vp, ct.c_int, i32, vp, vp, vp, i64, vp, vp, vp, vp]
+    L.ftsb_solve_dc.restype = ct.c_int
     L.ftsb_run_tran.argtypes = [vp, d, d, ct.POINTER(FtsbTranOpts), vp, vp, vp, vp, vp, vp, ct.c_int]
     L.ftsb_run_tran.restype = ct.c_int
     L.ftsb_sync.argtypes = [vp]

@@ -95,6 +95,14 @@ struct ftsb_circuit {
                            // structure allows it; 2: always try; 0: never
     int slots_global = 1;  // 1: large circuits keep the slot table and the solution vectors in L2-resident global scratch
     int fill_cap = 0;      // >0: run-time fill-in pool entries per instance of those kernels (0 = automatic)
+    // pipelined host-buffer entry points (ftsb_solve_op / ftsb_solve_dc): one stream and one work counter per chunk
+    static constexpr int PIPE_MAX = 8;
+    cudaStream_t pipe[PIPE_MAX] = {};
+    cudaEvent_t pipe_ev[PIPE_MAX] = {}, pipe_ev0 = nullptr;
+    bool pipe_ready = false;
+    int pipe_chunks = 4; // chunks per call (option "pipe_chunks"; 1 = serial copies)
+    DevBuf pipe_work;
+    unsigned long long pipe_begin[PIPE_MAX] = {};
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
                            // 2-3 warps per SM in shared memory and is latency bound)
@@ -639,20 +647,29 @@ bool ensure_jit(ftsb_circuit *c, int an)
     return true;
 }
 
-int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
+// Launches the per-topology kernel over instances [begin, end) on `stream`: `work` (already holding `begin`) hands out
+// global instance indices and the kernel's batch bound is `end`, so several ranges can be in flight on different
+// streams with one shared redo list and one set of counters.
+int launch_jit_range(ftsb_circuit *c, int an, RunArgs &a, cudaStream_t stream, unsigned long long *work, long long begin,
+                     long long end)
 {
-    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
     const std::vector<int> &ib = c->comp.ints();
     int sweep_slot = an == AN_DC ? ib[c->comp.off_src + 5 * a.sweep_src + 1] : 0;
     const double *vals = a.vals, *fn = a.fn, *st = a.start, *sp = a.stop, *se = a.step;
-    long long batch = a.batch, max_points = a.max_points;
-    void *params[] = {&vals, &fn, &batch, &a.work, &a.counters, &a.x, &a.n_iters, &a.status, &a.redo_list, &a.redo_count,
+    long long batch = end, max_points = a.max_points;
+    void *params[] = {&vals, &fn, &batch, &work, &a.counters, &a.x, &a.n_iters, &a.status, &a.redo_list, &a.redo_count,
                       &st, &sp, &se, &max_points, &a.points_done, &sweep_slot};
-    const int grid = (int)std::max(1LL, std::min((a.batch + 31) / 32, (long long)c->jit_occ[an] * c->sm_count));
+    const int grid = (int)std::max(1LL, std::min((end - begin + 31) / 32, (long long)c->jit_occ[an] * c->sm_count));
     std::string err;
-    if (!jit_launch(c->jit[an], grid, (void *)c->stream, params, err)) return fail(c, FTSB_E_CUDA, err);
+    if (!jit_launch(c->jit[an], grid, (void *)stream, params, err)) return fail(c, FTSB_E_CUDA, err);
     c->launches++;
     return 0;
+}
+
+int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
+{
+    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+    return launch_jit_range(c, an, a, c->stream, a.work, 0, a.batch);
 }
 
 // one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
@@ -886,6 +903,15 @@ void ftsb_destroy(ftsb_circuit *c)
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    if (c->pipe_ready) {
+        for (int k = 0; k < ftsb_circuit::PIPE_MAX; ++k) {
+            cudaStreamSynchronize(c->pipe[k]);
+            cudaStreamDestroy(c->pipe[k]);
+            cudaEventDestroy(c->pipe_ev[k]);
+        }
+        cudaEventDestroy(c->pipe_ev0);
+    }
+    c->pipe_work.release();
     DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
                       &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
                       &c->s_st, &c->redo, &c->plan_buf[0], &c->plan_buf[1], &c->trace};
@@ -931,6 +957,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
+    else if (!strcmp(name, "pipe_chunks"))
+        c->pipe_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(value, ftsb_circuit::PIPE_MAX));
     else
         return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
     return 0;
@@ -1075,6 +1103,197 @@ int ftsb_run_dc(ftsb_circuit *c, int32_t sweep_elem, const double *start, const 
         FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     return 0;
+}
+
+// ---- pipelined host-buffer entry points ------------------------------------------------------------------
+// ftsb_set_params + ftsb_run_op / ftsb_run_dc in one blocking call.  When the handle is in its steady state on the
+// per-topology kernel (plans learned, kernel loaded, nothing left to relearn) the batch is cut into chunks, each on
+// its own stream: host->device copy of the chunk's parameters, the kernel over the chunk's instance range (global
+// indices, one shared redo list), device->host copy of the chunk's results.  Chunk kernels co-reside, so the SMs stay
+// as full as with one launch while the copies of the neighbouring chunks run on the copy engines.  Instances the
+// kernel abandoned are redone by the dense kernel afterwards and the outputs copied again (rare).  In every other
+// state (first calls of a handle, other kernel families, parameter-major input) the two serial calls run instead.
+} // extern "C"
+
+namespace {
+
+bool jit_steady(const ftsb_circuit *c, int an, long long batch)
+{
+    return (an == AN_OP || an == AN_DC) && c->plan_state[an] == 1 && c->jit_state[an] == 1 && c->relearn_left[an] == 0 &&
+           c->jit_opt && c->skip_refactor && c->plan_opt && !c->force_generic && !c->force_cta && !c->sparse && c->lanes <= 0 &&
+           std::max(c->comp.n_start, 1) <= 16 && batch >= 4096 && c->pipe_chunks > 1;
+}
+
+int pipe_init(ftsb_circuit *c)
+{
+    if (c->pipe_ready) return 0;
+    for (int k = 0; k < ftsb_circuit::PIPE_MAX; ++k) {
+        FTSB_CUDA(c, cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
+        FTSB_CUDA(c, cudaEventCreateWithFlags(&c->pipe_ev[k], cudaEventDisableTiming));
+    }
+    FTSB_CUDA(c, cudaEventCreateWithFlags(&c->pipe_ev0, cudaEventDisableTiming));
+    FTSB_CUDA(c, c->pipe_work.ensure(ftsb_circuit::PIPE_MAX * 8));
+    c->pipe_ready = true;
+    return 0;
+}
+
+struct PipeIo { // host buffers of one call
+    const double *vals, *fn, *start, *stop, *step;
+    double *x;
+    int32_t *n_iters, *status;
+    int64_t *points_done;
+    long long P; // points per instance (.op: 1)
+};
+
+int solve_pipelined(ftsb_circuit *c, int an, long long B, const PipeIo &io, int sweep_src)
+{
+    int rc = pipe_init(c);
+    if (rc) return rc;
+    const int ne = c->comp.n_elems, nf = c->comp.n_fn;
+    const int n = an == AN_OP ? c->comp.n_start : c->comp.n_run;
+    const long long P = io.P;
+    FTSB_CUDA(c, c->vals.ensure((size_t)B * std::max(ne, 1) * 8));
+    FTSB_CUDA(c, c->fn.ensure((size_t)B * std::max(nf, 1) * 7 * 8));
+    FTSB_CUDA(c, c->o_x.ensure((size_t)B * P * std::max(n, 1) * 8));
+    FTSB_CUDA(c, c->o_it.ensure((size_t)B * P * 4));
+    FTSB_CUDA(c, c->o_status.ensure((size_t)B * 4));
+    FTSB_CUDA(c, c->redo.ensure((size_t)B * 8));
+    if (an == AN_DC) {
+        FTSB_CUDA(c, c->i_start.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->i_stop.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->i_step.ensure((size_t)B * 8));
+        FTSB_CUDA(c, c->o_done.ensure((size_t)B * 8));
+    }
+    c->batch = B;
+    RunArgs a{};
+    a.prog = c->prog;
+    a.batch = B;
+    a.vals = (const double *)c->vals.p;
+    a.fn = (const double *)c->fn.p;
+    a.work = (unsigned long long *)c->work.p;
+    a.counters = (unsigned long long *)c->counters.p;
+    a.skip_refactor = c->skip_refactor;
+    a.x = (double *)c->o_x.p;
+    a.n_iters = (int *)c->o_it.p;
+    a.status = (int *)c->o_status.p;
+    a.sweep_src = sweep_src;
+    a.max_points = P;
+    a.start = (const double *)c->i_start.p;
+    a.stop = (const double *)c->i_stop.p;
+    a.step = (const double *)c->i_step.p;
+    a.points_done = (long long *)c->o_done.p;
+    a.redo_list = (long long *)c->redo.p;
+    a.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
+    // the dense kernel that takes the redo list
+    LaunchPlan pd;
+    rc = plan_launch(c, an, B, pd);
+    if (rc) return rc;
+    const std::string dv = c->variant;
+    if (pd.scratch_bytes) FTSB_CUDA(c, c->scratch.ensure(pd.scratch_bytes));
+    a.scratch = (double *)c->scratch.p;
+
+    // chunks: equal, multiples of 32 instances
+    int K = c->pipe_chunks;
+    long long chunk = ((B + K - 1) / K + 31) / 32 * 32;
+    chunk = std::max(chunk, 2048LL);
+    K = (int)((B + chunk - 1) / chunk);
+    for (int k = 0; k < K; ++k) c->pipe_begin[k] = (unsigned long long)(k * chunk);
+    FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
+    FTSB_CUDA(c, cudaMemcpyAsync(c->pipe_work.p, c->pipe_begin, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    FTSB_CUDA(c, cudaEventRecord(c->pipe_ev0, c->stream));
+    auto d2h = [&](cudaStream_t s, long long b0, long long cnt) -> int {
+        FTSB_CUDA(c, cudaMemcpyAsync(io.x + b0 * P * n, a.x + b0 * P * n, (size_t)cnt * P * n * 8, cudaMemcpyDeviceToHost, s));
+        FTSB_CUDA(c, cudaMemcpyAsync(io.n_iters + b0 * P, a.n_iters + b0 * P, (size_t)cnt * P * 4, cudaMemcpyDeviceToHost, s));
+        FTSB_CUDA(c, cudaMemcpyAsync(io.status + b0, a.status + b0, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s));
+        if (an == AN_DC)
+            FTSB_CUDA(c, cudaMemcpyAsync(io.points_done + b0, a.points_done + b0, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    for (int k = 0; k < K; ++k) {
+        cudaStream_t s = c->pipe[k];
+        const long long b0 = k * chunk, b1 = std::min(B, b0 + chunk), cnt = b1 - b0;
+        FTSB_CUDA(c, cudaStreamWaitEvent(s, c->pipe_ev0, 0));
+        if (ne > 0)
+            FTSB_CUDA(c, cudaMemcpyAsync((double *)c->vals.p + b0 * ne, io.vals + b0 * ne, (size_t)cnt * ne * 8, cudaMemcpyHostToDevice, s));
+        if (nf > 0)
+            FTSB_CUDA(c, cudaMemcpyAsync((double *)c->fn.p + b0 * nf * 7, io.fn + b0 * nf * 7, (size_t)cnt * nf * 56, cudaMemcpyHostToDevice, s));
+        if (an == AN_DC) {
+            FTSB_CUDA(c, cudaMemcpyAsync((double *)c->i_start.p + b0, io.start + b0, (size_t)cnt * 8, cudaMemcpyHostToDevice, s));
+            FTSB_CUDA(c, cudaMemcpyAsync((double *)c->i_stop.p + b0, io.stop + b0, (size_t)cnt * 8, cudaMemcpyHostToDevice, s));
+            FTSB_CUDA(c, cudaMemcpyAsync((double *)c->i_step.p + b0, io.step + b0, (size_t)cnt * 8, cudaMemcpyHostToDevice, s));
+            FTSB_CUDA(c, cudaMemsetAsync(a.n_iters + b0 * P, 0, (size_t)cnt * P * 4, s));
+            FTSB_CUDA(c, cudaMemsetAsync(a.x + b0 * P * n, 0, (size_t)cnt * P * n * 8, s));
+        }
+        rc = launch_jit_range(c, an, a, s, (unsigned long long *)c->pipe_work.p + k, b0, b1);
+        if (rc) return rc;
+        rc = d2h(s, b0, cnt);
+        if (rc) return rc;
+        FTSB_CUDA(c, cudaEventRecord(c->pipe_ev[k], s));
+    }
+    for (int k = 0; k < K; ++k) FTSB_CUDA(c, cudaStreamWaitEvent(c->stream, c->pipe_ev[k], 0));
+    // dense redo pass over whatever the chunk kernels abandoned (an empty list almost always)
+    RunArgs ar = a;
+    ar.in_list = a.redo_list;
+    ar.in_count = a.redo_count;
+    ar.prog.lay = pd.lay;
+    rc = launch_kernel(c, pd, ar);
+    if (rc) return rc;
+    unsigned long long n_redo = 0;
+    FTSB_CUDA(c, cudaMemcpyAsync(&n_redo, a.redo_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (n_redo) {
+        rc = d2h(c->stream, 0, B);
+        if (rc) return rc;
+        FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    const PlanHost &ph = c->plan_host[an];
+    c->last_plan_an = an;
+    c->last_redo_an = -1;
+    c->variant = "jit" + std::to_string(ph.K) + "n" + std::to_string(ph.n) + "/S" + std::to_string(ph.S) + "/r" +
+                 std::to_string(c->jit[an].regs) + "/occ" + std::to_string(c->jit_occ[an]) + "/pipe" + std::to_string(K) + "+redo:" + dv;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int ftsb_solve_op(ftsb_circuit *c, int64_t batch, const double *vals, const double *fn, int layout, double *x,
+                  int32_t *n_iters, int32_t *status)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    if (!x || !n_iters || !status) return fail(c, FTSB_E_ARG, "ftsb_solve_op: null output");
+    if (batch > 0 && layout == FTSB_LAYOUT_INSTANCE_MAJOR && (c->comp.n_elems == 0 || vals) && (c->comp.n_fn == 0 || fn) &&
+        jit_steady(c, AN_OP, batch)) {
+        FTSB_CUDA(c, cudaSetDevice(c->device));
+        PipeIo io{vals, fn, nullptr, nullptr, nullptr, x, n_iters, status, nullptr, 1};
+        return solve_pipelined(c, AN_OP, batch, io, 0);
+    }
+    int rc = ftsb_set_params(c, batch, vals, fn, layout, FTSB_MEM_HOST);
+    if (rc) return rc;
+    return ftsb_run_op(c, x, n_iters, status, FTSB_MEM_HOST);
+}
+
+int ftsb_solve_dc(ftsb_circuit *c, int64_t batch, const double *vals, const double *fn, int layout, int32_t sweep_elem,
+                  const double *start, const double *stop, const double *step, int64_t max_points, double *x,
+                  int32_t *n_iters, int64_t *points_done, int32_t *status)
+{
+    if (!c) return fail(nullptr, FTSB_E_ARG, "null handle");
+    if (batch > 0 && layout == FTSB_LAYOUT_INSTANCE_MAJOR && (c->comp.n_elems == 0 || vals) && (c->comp.n_fn == 0 || fn) &&
+        start && stop && step && x && n_iters && points_done && status && max_points > 0 && sweep_elem >= 0 &&
+        sweep_elem < c->comp.n_elems && c->comp.src_of_elem[sweep_elem] >= 0 && jit_steady(c, AN_DC, batch)) {
+        for (long long i = 0; i < batch; ++i) {
+            double cnt = std::ceil((stop[i] - start[i]) / step[i]);
+            if (cnt > (double)max_points)
+                return fail(c, FTSB_E_ARG, "ftsb_solve_dc: instance " + std::to_string(i) + " has more than max_points points");
+        }
+        FTSB_CUDA(c, cudaSetDevice(c->device));
+        PipeIo io{vals, fn, start, stop, step, x, n_iters, status, points_done, (long long)max_points};
+        return solve_pipelined(c, AN_DC, batch, io, c->comp.src_of_elem[sweep_elem]);
+    }
+    int rc = ftsb_set_params(c, batch, vals, fn, layout, FTSB_MEM_HOST);
+    if (rc) return rc;
+    return ftsb_run_dc(c, sweep_elem, start, stop, step, max_points, x, n_iters, points_done, status, FTSB_MEM_HOST);
 }
 
 int ftsb_run_tran(ftsb_circuit *c, double stop, double step_max, const ftsb_tran_opts *opts, double *t, double *x,

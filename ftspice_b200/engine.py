@@ -240,6 +240,55 @@ class BatchEngine:
                                             _ptr(nrec), _ptr(xf), _ptr(st), capi.MEM_HOST), self.h)
         return TranResult(st, nrec, it, t, x, xf)
 
+    # ---- parameters + analysis in one call (host buffers; chunk-pipelined copies once the handle is warm) ----
+    def _host_params(self, vals: np.ndarray, fns: Optional[np.ndarray]):
+        c = self.circ
+        vals = np.ascontiguousarray(vals, np.float64)
+        B = vals.shape[0]
+        if fns is None:
+            fns = np.broadcast_to(c.fns, (B, c.n_elems, 7))
+        fns = np.asarray(fns)
+        if fns.shape[1] == c.n_elems:
+            fns = fns[:, self.fn_elems, :]
+        elif fns.shape[1] != self.n_fn:
+            raise ValueError(f"fns must be [B, {c.n_elems}, 7] or [B, {self.n_fn}, 7]")
+        return vals, np.ascontiguousarray(fns, np.float64), B
+
+    def solve_op(self, vals: np.ndarray, fns: Optional[np.ndarray] = None) -> OpResult:
+        """ftsb_solve_op: same results as set_params(vals, fns) followed by run_op()."""
+        vals, fns, B = self._host_params(vals, fns)
+        n = self.circ.n_start
+        x = np.zeros((B, n))
+        it = np.zeros(B, np.int32)
+        st = np.zeros(B, np.int32)
+        capi.check(capi.lib().ftsb_solve_op(self.h, B, _ptr(vals), _ptr(fns) if self.n_fn else None,
+                                            capi.LAYOUT_INSTANCE_MAJOR, _ptr(x), _ptr(it), _ptr(st)), self.h)
+        self.batch = B
+        return OpResult(st, it, x)
+
+    def solve_dc(self, vals: np.ndarray, fns: Optional[np.ndarray], source: Union[str, int], start, stop, step,
+                 max_points: Optional[int] = None) -> DcResult:
+        """ftsb_solve_dc: same results as set_params(vals, fns) followed by run_dc(...)."""
+        vals, fns, B = self._host_params(vals, fns)
+        n = self.circ.n_run
+        se = self.circ.elem_index(source) if isinstance(source, str) else int(source)
+        start = np.ascontiguousarray(np.broadcast_to(np.asarray(start, np.float64), (B,)))
+        stop = np.ascontiguousarray(np.broadcast_to(np.asarray(stop, np.float64), (B,)))
+        step = np.ascontiguousarray(np.broadcast_to(np.asarray(step, np.float64), (B,)))
+        counts = np.ceil((stop - start) / step)
+        counts = np.where(counts >= 0, counts, 0).astype(np.int64)
+        P = int(max_points or max(int(counts.max()), 1))
+        x = np.zeros((B, P, n))
+        it = np.zeros((B, P), np.int32)
+        done = np.zeros(B, np.int64)
+        st = np.zeros(B, np.int32)
+        capi.check(capi.lib().ftsb_solve_dc(self.h, B, _ptr(vals), _ptr(fns) if self.n_fn else None,
+                                            capi.LAYOUT_INSTANCE_MAJOR, se, _ptr(start), _ptr(stop), _ptr(step), P,
+                                            _ptr(x), _ptr(it), _ptr(done), _ptr(st)), self.h)
+        self.batch = B
+        sweep = start[:, None] + step[:, None] * np.arange(P, dtype=np.float64)[None, :]
+        return DcResult(st, done, it, x, sweep)
+
     # ---- analyses (device pointers; asynchronous on the handle's stream) ----
     def run_op_device(self, x_ptr: int, it_ptr: int, st_ptr: int) -> None:
         capi.check(capi.lib().ftsb_run_op(self.h, ct.c_void_p(x_ptr), ct.c_void_p(it_ptr), ct.c_void_p(st_ptr),

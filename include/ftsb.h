@@ -155,6 +155,18 @@ int ftsb_run_op(ftsb_circuit *c, double *x, int32_t *n_iters, int32_t *status, i
 int ftsb_run_dc(ftsb_circuit *c, int32_t sweep_elem, const double *start, const double *stop, const double *step,
                 int64_t max_points, double *x, int32_t *n_iters, int64_t *points_done, int32_t *status, int mem);
 
+/* ---- Engine::new values + Engine::run_op / run_dc in one blocking call, HOST buffers only ----
+ * Same results as ftsb_set_params(..., FTSB_MEM_HOST) followed by ftsb_run_op / ftsb_run_dc(..., FTSB_MEM_HOST)
+ * (src/engine.rs:31-60 then :62-90 / :92-140).  Once a handle runs its per-topology kernel (small circuits, from
+ * the third call on) the batch is processed in chunks on separate streams so that the host<->device copies of one
+ * chunk overlap the solve of the others (option "pipe_chunks", default 4; 1 = serial); pass page-locked buffers
+ * for the copies to be asynchronous.  Instance-major layout pipelines; parameter-major takes the serial path. */
+int ftsb_solve_op(ftsb_circuit *c, int64_t batch, const double *vals, const double *fn, int layout, double *x,
+                  int32_t *n_iters, int32_t *status);
+int ftsb_solve_dc(ftsb_circuit *c, int64_t batch, const double *vals, const double *fn, int layout, int32_t sweep_elem,
+                  const double *start, const double *stop, const double *step, int64_t max_points, double *x,
+                  int32_t *n_iters, int64_t *points_done, int32_t *status);
+
 /* ---- Engine::run_tran ----  (.TRAN stop step: start is always 0, src/parser.rs:246-250)
  * t[batch][capacity], x[batch][capacity][n_run], n_iters[batch][capacity] (any may be NULL),
  * n_rec[batch] = accepted steps, x_final[batch][n_run] = unknowns at the last accepted step (may be

@@ -798,3 +798,76 @@ def test_jit_kernel_random_circuits(seed, oracle_mod):
         kk = int(done[i])
         assert (outs["jit"][1][5][i, :kk] == dit[i, :kk]).all()
         assert_close(outs["jit"][1][6][i, :kk], dx[i, :kk], f"random circuit {seed} .dc chain {i}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# pipelined host-buffer entry points (ftsb_solve_op / ftsb_solve_dc): chunks on separate streams
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which,rel,B", [("proj1_nl", 0.1, 20000), ("proj1_nl", 0.45, 9001), ("npn_test", 0.3, 4100)])
+def test_solve_op_pipelined_equals_serial_bitwise(which, rel, B):
+    """ftsb_solve_op = set_params + run_op.  From the third call on the handle is warm and the batch goes through in
+    chunks on separate streams with one shared redo list (a zero-ohm resistor in every 37th instance gives an infinite
+    pivot candidate: those instances go to the dense kernel): every output and every counter must equal the serial
+    path's, whatever the chunk count, also with a ragged last chunk."""
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else load(which)
+    vals, fns = nl.monte_carlo(circ, B, rel=rel)
+    if rel > 0.4:
+        vals[::37, int(np.flatnonzero(np.asarray(circ.kind) == nl.R)[0])] = 0.0
+    ref = BatchEngine(circ)
+    ref.set_params(vals, fns)
+    r0 = ref.run_op()
+    c0 = ref.counters()
+    be = BatchEngine(circ)
+    for chunks in (4, 4, 4, 2, 8, 3):
+        be.set_option("pipe_chunks", chunks)
+        r = be.solve_op(vals, fns)
+        c = be.counters()
+        assert np.array_equal(r.x, r0.x, equal_nan=True) and np.array_equal(r.n_iters, r0.n_iters)
+        assert np.array_equal(r.status, r0.status)
+        for k in ("solve_points", "newton_iters", "lu_factor", "lu_solve"):
+            assert c[k] == c0[k], (k, c, c0, be.variant)
+    assert "/pipe" in be.variant, be.variant
+    if rel > 0.4:
+        assert c["redo"] >= (B + 36) // 37, c  # the shared redo list of the chunk kernels was exercised
+    # a different batch through the warm handle (buffers grow, chunk bounds move)
+    vals2, fns2 = nl.monte_carlo(circ, B + 777, rel=rel, seed=7)
+    r = be.solve_op(vals2, fns2)
+    ref.set_params(vals2, fns2)
+    r1 = ref.run_op()
+    assert np.array_equal(r.x, r1.x, equal_nan=True) and np.array_equal(r.n_iters, r1.n_iters)
+    assert np.array_equal(r.status, r1.status)
+
+
+def test_solve_dc_pipelined_equals_serial_bitwise():
+    circ = load("nmos_test")
+    C, Lp = 6000, 12
+    width = 3.6 / C  # crosses the 3.48 V failure (Q18): those chains stop early
+    start = np.arange(C) * width
+    step = np.full(C, width / Lp)
+    stop = start + width - 0.25 * step
+    vals = np.broadcast_to(circ.vals, (C, circ.n_elems)).copy()
+    se = circ.elem_index("V01")
+    ref = BatchEngine(circ)
+    ref.set_params(vals)
+    r0 = ref.run_dc(se, start, stop, step, max_points=Lp)
+    be = BatchEngine(circ)
+    for chunks in (4, 4, 4, 2):
+        be.set_option("pipe_chunks", chunks)
+        r = be.solve_dc(vals, None, se, start, stop, step, max_points=Lp)
+        for a, b in ((r.status, r0.status), (r.points_done, r0.points_done), (r.n_iters, r0.n_iters), (r.x, r0.x)):
+            assert np.array_equal(a, b, equal_nan=True)
+    assert "/pipe" in be.variant, be.variant
+    assert (r0.status != 0).any() and (r0.status == 0).any()
+
+
+def test_solve_op_small_batch_and_param_major_take_the_serial_path():
+    circ = nl.load(nl.PROJ1_NL)
+    vals, fns = nl.monte_carlo(circ, 300)
+    be = BatchEngine(circ)
+    ref = BatchEngine(circ)
+    ref.set_params(vals, fns)
+    r0 = ref.run_op()
+    for _ in range(3):
+        r = be.solve_op(vals, fns)
+        assert np.array_equal(r.x, r0.x) and np.array_equal(r.n_iters, r0.n_iters)
+    assert "/pipe" not in be.variant
