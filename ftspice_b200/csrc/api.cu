@@ -79,6 +79,7 @@ struct ftsb_circuit {
     int jit_state[2] = {0, 0}; // 0 = not tried, 1 = loaded, -1 = unavailable (NVRTC / driver missing, compile error)
     int jit_occ[2] = {0, 0};
     int jit_opt = 1;
+    int jit_log1p = 1;      // 1: generated kernels use fts_log1p.h like the built kernels; 0: CUDA's log1p (A/B measurements)
     int jit_min_blocks = 1; // __launch_bounds__(32, this): register cap of the generated kernel
     int last_plan_an = -1;  // analysis mode of the last run when it used the plan / JIT kernels (flop accounting)
     std::string jit_msg;
@@ -614,7 +615,7 @@ bool ensure_jit(ftsb_circuit *c, int an)
     if (c->jit_state[an] != 0) return c->jit_state[an] == 1;
     c->jit_state[an] = -1;
     const PlanHost &ph = c->plan_host[an];
-    const std::string src = jit_source(c->comp, an, ph) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
+    const std::string src = jit_source(c->comp, an, ph, c->jit_log1p != 0) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
     std::string cubin, err;
     {
         // the same topology + plans give the same source: compile once per process
@@ -632,7 +633,7 @@ bool ensure_jit(ftsb_circuit *c, int an)
             cache[src] = cubin;
         }
     }
-    const int smem = ph.S * 32 * 8;
+    const int smem = jit_smem_bytes(ph);
     if ((size_t)smem > c->smem_optin || !jit_load(cubin, smem, c->jit[an], err)) {
         c->jit_msg = err;
         return false;
@@ -957,7 +958,13 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
-    else if (!strcmp(name, "pipe_chunks"))
+    else if (!strcmp(name, "jit_log1p")) {
+        c->jit_log1p = value ? 1 : 0;
+        for (int an = 0; an < 2; ++an) { // regenerate on demand
+            jit_unload(c->jit[an]);
+            c->jit_state[an] = 0;
+        }
+    } else if (!strcmp(name, "pipe_chunks"))
         c->pipe_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(value, ftsb_circuit::PIPE_MAX));
     else
         return fail(c, FTSB_E_ARG, std::string("ftsb_set_option: unknown option ") + name);
@@ -1564,6 +1571,33 @@ extern "C" double ftsb_measure_fp64_tflops(int device)
     return best;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// diagnostics (not part of include/ftsb.h): the damping's ln_1p (fts_log1p.h) evaluated on the device and on the host
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_debug_log1p(const double *in, double *out, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = damp_log1p(in[i]);
+}
+} // namespace
+
+extern "C" int ftsb_debug_log1p(int device, int64_t n, const double *in, double *out)
+{
+    if (device < 0) { // host evaluation of the same header
+        alignas(16) static const unsigned long long tab[2 * FTS_LOG1P_N] = {FTS_LOG1P_TABLE};
+        for (int64_t i = 0; i < n; ++i) out[i] = fts_log1p_pos(in[i], reinterpret_cast<const double *>(tab));
+        return 0;
+    }
+    double *d = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&d, (size_t)n * 16) != cudaSuccess) return FTSB_E_CUDA;
+    cudaMemcpy(d, in, (size_t)n * 8, cudaMemcpyHostToDevice);
+    k_debug_log1p<<<592, 256>>>(d, d + n, (long long)n);
+    cudaError_t e = cudaMemcpy(out, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : FTSB_E_CUDA;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // diagnostics (not part of include/ftsb.h): generate + compile the per-topology kernel without a GPU

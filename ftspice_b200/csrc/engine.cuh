@@ -18,7 +18,15 @@
 #include "plan.h"
 #include "prog.h"
 
+#include "log1p_tab.h"
+#include "fts_log1p.h"
+
 namespace ftsb {
+
+// ln_1p of the damped Newton step (newtons_method.rs:73-77) for its non-negative argument: fts_log1p.h
+static __device__ __align__(16) const unsigned long long k_log1p_tab[2 * FTS_LOG1P_N] = {FTS_LOG1P_TABLE};
+__device__ __forceinline__ double damp_log1p(double u) { return fts_log1p_pos(u, reinterpret_cast<const double *>(k_log1p_tab)); }
+
 
 // ---------------------------------------------------------------------------------------------------------
 // kernel arguments
@@ -643,7 +651,7 @@ __device__ int SmemSolver<Team>::newton(const Team &tm, const ModeProg &M, const
         double qv = 0.0, qi = 0.0;
         for (int i = tm.rank; i < n; i += tm.size()) {
             double d = w.xp[i] - w.x[i];
-            double t = (1.3 / 16.0) * copysign(1.0, d) * log1p(16.0 * fabs(d));
+            double t = (1.3 / 16.0) * copysign(1.0, d) * damp_log1p(16.0 * fabs(d));
             if (d != d) t = d;
             w.xn[i] = w.x[i] + t;
             double t2 = t * t;

@@ -18,7 +18,11 @@
 namespace ftsb {
 
 // CUDA C++ source of the specialised kernel `ftsb_jit` for analysis `an` (AN_OP or AN_DC)
-std::string jit_source(const Compiled &comp, int an, const PlanHost &ph);
+// fast_log1p: the damping's ln_1p is fts_log1p.h (table in shared memory behind the matrix entries) like every other
+// kernel of the library; false = CUDA's log1p (A/B measurements only: results differ in the last bit)
+std::string jit_source(const Compiled &comp, int an, const PlanHost &ph, bool fast_log1p = true);
+// dynamic shared memory of the generated kernel
+int jit_smem_bytes(const PlanHost &ph);
 
 struct JitKernel {
     void *module = nullptr;   // CUmodule

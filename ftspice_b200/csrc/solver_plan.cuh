@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(32) k_plan(const __grid_constant__ RunArgs a)
         for (int i = ts.rank; i < n; i += G) { // damped step (newtons_method.rs:73-77)
             const double xi = w.x[i];
             const double d = xpp[i * TS] - xi;
-            const double t = (1.3 / 16.0) * copysign(1.0, d) * log1p(16.0 * fabs(d));
+            const double t = (1.3 / 16.0) * copysign(1.0, d) * damp_log1p(16.0 * fabs(d));
             w.xn[i] = xi + t;
             if (__ldg(&M.cls[i]))
                 qi += t * t;

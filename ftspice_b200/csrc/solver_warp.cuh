@@ -227,7 +227,7 @@ struct WarpSolver {
             for (int i = tm.rank; i < n; i += 32) { // damped step (newtons_method.rs:73-77)
                 const double xi = w.x[i];
                 const double d = xp[i] - xi;
-                const double t = (1.3 / 16.0) * copysign(1.0, d) * log1p(16.0 * fabs(d));
+                const double t = (1.3 / 16.0) * copysign(1.0, d) * damp_log1p(16.0 * fabs(d));
                 w.xn[i] = xi + t;
                 if (__ldg(&M.cls[i]))
                     qi += t * t;

@@ -871,3 +871,11 @@ def test_solve_op_small_batch_and_param_major_take_the_serial_path():
         r = be.solve_op(vals, fns)
         assert np.array_equal(r.x, r0.x) and np.array_equal(r.n_iters, r0.n_iters)
     assert "/pipe" not in be.variant
+
+
+def test_log1p_device_equals_host_bitwise():
+    """The damping's ln_1p (fts_log1p.h) is IEEE adds / multiplies / FMAs only: the device must return the bits the
+    host evaluation of the same header returns (whose accuracy tests/test_log1p.py pins)."""
+    from test_log1p import log1p_host, sample
+    u = np.concatenate([sample(seed=5), [np.inf, np.nan]])
+    assert np.array_equal(log1p_host(u, device=0), log1p_host(u, device=-1), equal_nan=True)
