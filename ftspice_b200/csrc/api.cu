@@ -615,7 +615,7 @@ bool ensure_jit(ftsb_circuit *c, int an)
     if (c->jit_state[an] != 0) return c->jit_state[an] == 1;
     c->jit_state[an] = -1;
     const PlanHost &ph = c->plan_host[an];
-    const std::string src = jit_source(c->comp, an, ph, c->jit_log1p != 0) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
+    const std::string src = jit_source(c->comp, an, ph, c->jit_log1p) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
     std::string cubin, err;
     {
         // the same topology + plans give the same source: compile once per process
@@ -959,7 +959,7 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
     else if (!strcmp(name, "jit_log1p")) {
-        c->jit_log1p = value ? 1 : 0;
+        c->jit_log1p = (int)std::max<int64_t>(0, std::min<int64_t>(value, 3));
         for (int an = 0; an < 2; ++an) { // regenerate on demand
             jit_unload(c->jit[an]);
             c->jit_state[an] = 0;
@@ -1597,6 +1597,32 @@ extern "C" int ftsb_debug_log1p(int device, int64_t n, const double *in, double 
     cudaError_t e = cudaMemcpy(out, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? 0 : FTSB_E_CUDA;
+}
+
+namespace {
+__global__ void k_debug_exp_pair(const double *in, double *e, double *m, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dev_exp_pair(in[i], e[i], m[i]);
+}
+} // namespace
+
+// exp / exp_m1 pair of the junction models (fts_exp.h); device < 0: host evaluation of the same header
+extern "C" int ftsb_debug_exp_pair(int device, int64_t n, const double *in, double *e, double *m)
+{
+    if (device < 0) {
+        alignas(16) static const unsigned long long tab[2 * FTS_EXP_N] = {FTS_EXP_TABLE};
+        for (int64_t i = 0; i < n; ++i) fts_exp_pair(in[i], reinterpret_cast<const double *>(tab), e + i, m + i);
+        return 0;
+    }
+    double *d = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&d, (size_t)n * 24) != cudaSuccess) return FTSB_E_CUDA;
+    cudaMemcpy(d, in, (size_t)n * 8, cudaMemcpyHostToDevice);
+    k_debug_exp_pair<<<592, 256>>>(d, d + n, d + 2 * n, (long long)n);
+    cudaError_t e1 = cudaMemcpy(e, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e2 = cudaMemcpy(m, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e1 == cudaSuccess && e2 == cudaSuccess ? 0 : FTSB_E_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -19,8 +19,9 @@ namespace ftsb {
 
 // CUDA C++ source of the specialised kernel `ftsb_jit` for analysis `an` (AN_OP or AN_DC)
 // fast_log1p: the damping's ln_1p is fts_log1p.h (table in shared memory behind the matrix entries) like every other
-// kernel of the library; false = CUDA's log1p (A/B measurements only: results differ in the last bit)
-std::string jit_source(const Compiled &comp, int an, const PlanHost &ph, bool fast_log1p = true);
+// kernel of the library (1: out-of-line, four unknowns per call; 3: out-of-line, one per call; 2: inlined at every unknown); 0 = CUDA's log1p (A/B measurements
+// only: results differ in the last bit)
+std::string jit_source(const Compiled &comp, int an, const PlanHost &ph, int fast_log1p = 1);
 // dynamic shared memory of the generated kernel
 int jit_smem_bytes(const PlanHost &ph);
 
