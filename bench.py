@@ -203,7 +203,7 @@ def dc_ranges(wl, count: int, first: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 50 for c2/c3, 3 for the .tran workloads)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="batch-size multiplier (1.0 = the named config)")
@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (e.g. lanes=2, force_generic=1)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 50 if args.workload in ("c2", "c3") else 3
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
 

@@ -1599,32 +1599,6 @@ extern "C" int ftsb_debug_log1p(int device, int64_t n, const double *in, double 
     return e == cudaSuccess ? 0 : FTSB_E_CUDA;
 }
 
-namespace {
-__global__ void k_debug_exp_pair(const double *in, double *e, double *m, long long n)
-{
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dev_exp_pair(in[i], e[i], m[i]);
-}
-} // namespace
-
-// exp / exp_m1 pair of the junction models (fts_exp.h); device < 0: host evaluation of the same header
-extern "C" int ftsb_debug_exp_pair(int device, int64_t n, const double *in, double *e, double *m)
-{
-    if (device < 0) {
-        alignas(16) static const unsigned long long tab[2 * FTS_EXP_N] = {FTS_EXP_TABLE};
-        for (int64_t i = 0; i < n; ++i) fts_exp_pair(in[i], reinterpret_cast<const double *>(tab), e + i, m + i);
-        return 0;
-    }
-    double *d = nullptr;
-    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&d, (size_t)n * 24) != cudaSuccess) return FTSB_E_CUDA;
-    cudaMemcpy(d, in, (size_t)n * 8, cudaMemcpyHostToDevice);
-    k_debug_exp_pair<<<592, 256>>>(d, d + n, d + 2 * n, (long long)n);
-    cudaError_t e1 = cudaMemcpy(e, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
-    cudaError_t e2 = cudaMemcpy(m, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    return e1 == cudaSuccess && e2 == cudaSuccess ? 0 : FTSB_E_CUDA;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // diagnostics (not part of include/ftsb.h): generate + compile the per-topology kernel without a GPU
 // ---------------------------------------------------------------------------------------------------------

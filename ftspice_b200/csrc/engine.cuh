@@ -20,20 +20,12 @@
 
 #include "log1p_tab.h"
 #include "fts_log1p.h"
-#include "exp_tab.h"
-#include "fts_exp.h"
 
 namespace ftsb {
 
 // ln_1p of the damped Newton step (newtons_method.rs:73-77) for its non-negative argument: fts_log1p.h
 static __device__ __align__(16) const unsigned long long k_log1p_tab[2 * FTS_LOG1P_N] = {FTS_LOG1P_TABLE};
 __device__ __forceinline__ double damp_log1p(double u) { return fts_log1p_pos(u, reinterpret_cast<const double *>(k_log1p_tab)); }
-// exp(a) and exp_m1(a) of a junction voltage (diode / NPN models) from one argument reduction: fts_exp.h
-static __device__ __align__(16) const unsigned long long k_exp_tab[2 * FTS_EXP_N] = {FTS_EXP_TABLE};
-__device__ __forceinline__ void dev_exp_pair(double a, double &e, double &m)
-{
-    fts_exp_pair(a, reinterpret_cast<const double *>(k_exp_tab), &e, &m);
-}
 
 
 // ---------------------------------------------------------------------------------------------------------
@@ -328,10 +320,8 @@ __device__ __forceinline__ int eval_device(const int *d, V x, V val)
         const double ISAT = 1.0e-12, NVT = 1.0 * 26e-3;
         double vd = xat(x, d[1]) - xat(x, d[2]);
         double arg = vd / NVT;
-        double ea, em1a;
-        dev_exp_pair(arg, ea, em1a);
-        double i = ISAT * em1a;
-        double g = ISAT / NVT * ea;
+        double i = ISAT * expm1(arg);
+        double g = ISAT / NVT * exp(arg);
         s[D_G] = g;
         s[D_IEQ] = i - g * vd;
         s[D_I] = i;
@@ -341,9 +331,7 @@ __device__ __forceinline__ int eval_device(const int *d, V x, V val)
         double vc = xat(x, d[1]), vb = xat(x, d[2]), ve = xat(x, d[3]);
         double vbe = vb - ve, vbc = vb - vc;
         double ae = vbe / VTE, ac = vbc / VTC;
-        double em1e, em1c, ee, ec;
-        dev_exp_pair(ae, ee, em1e);
-        dev_exp_pair(ac, ec, em1c);
+        double em1e = expm1(ae), em1c = expm1(ac), ee = exp(ae), ec = exp(ac);
         double ie = -IES * em1e + AR * ICS * em1c;
         double ic = AF * IES * em1e - ICS * em1c;
         double ib = -(ie + ic);
