@@ -16,7 +16,8 @@ struct StepBuild {
 };
 } // namespace
 
-bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair<uint64_t, long long>> perms, PlanHost &out)
+bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair<uint64_t, long long>> perms, PlanHost &out,
+                 int max_plans)
 {
     out = PlanHost();
     if (n < 2 || n > 16 || perms.empty()) return false;
@@ -51,7 +52,7 @@ bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair
     std::vector<std::vector<StepBuild>> plans;      // [plan][step]
     long long covered = 0;
     for (auto &pc : perms) {
-        if ((int)plans.size() >= PLAN_MAX) break;
+        if ((int)plans.size() >= std::min(PLAN_MAX, std::max(max_plans, 1))) break;
         std::vector<int> piv(n);
         unsigned seen = 0;
         for (int i = 0; i < n; ++i) {

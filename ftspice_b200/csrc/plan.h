@@ -44,6 +44,7 @@ struct PlanHost {
 
 // jfull_dst: J_full destinations (row | col << 16) in J_full order; perms: (nibble-packed position -> row, count),
 // any order.  Returns false when no usable plan exists (n < 2, n > 16, too many entries, inconsistent traces).
-bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair<uint64_t, long long>> perms, PlanHost &out);
+bool build_plans(int n, const std::vector<int> &jfull_dst, std::vector<std::pair<uint64_t, long long>> perms, PlanHost &out,
+                 int max_plans = PLAN_MAX);
 
 } // namespace ftsb
