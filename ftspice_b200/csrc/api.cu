@@ -81,6 +81,8 @@ struct ftsb_circuit {
     int jit_occ[2] = {0, 0};
     int jit_opt = 1;
     int jit_log1p = 1;      // 1: generated kernels use fts_log1p.h like the built kernels; 0: CUDA's log1p (A/B measurements)
+    int jit_max_regs = 0;   // > 0: __maxnreg__ of the generated kernel (instead of jit_min_blocks).  Measured: 224 / 216 registers
+                            // still give 2 warps per scheduler (16 K registers each): a third needs <= 168 and spills
     int jit_min_blocks = 1; // __launch_bounds__(32, this): register cap of the generated kernel
     int last_plan_an = -1;  // analysis mode of the last run when it used the plan / JIT kernels (flop accounting)
     std::string jit_msg;
@@ -616,7 +618,7 @@ bool ensure_jit(ftsb_circuit *c, int an)
     if (c->jit_state[an] != 0) return c->jit_state[an] == 1;
     c->jit_state[an] = -1;
     const PlanHost &ph = c->plan_host[an];
-    const std::string src = jit_source(c->comp, an, ph, c->jit_log1p) + "// min_blocks " + std::to_string(c->jit_min_blocks) + "\n";
+    const std::string src = jit_source(c->comp, an, ph, c->jit_log1p) + "// min_blocks " + std::to_string(c->jit_min_blocks) + " max_regs " + std::to_string(c->jit_max_regs) + "\n";
     std::string cubin, err;
     {
         // the same topology + plans give the same source: compile once per process
@@ -627,7 +629,7 @@ bool ensure_jit(ftsb_circuit *c, int an)
         if (it != cache.end())
             cubin = it->second;
         else {
-            if (!jit_compile(src, cubin, err, c->jit_min_blocks)) {
+            if (!jit_compile(src, cubin, err, c->jit_min_blocks, c->jit_max_regs)) {
                 c->jit_msg = err;
                 return false;
             }
@@ -961,6 +963,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
+    else if (!strcmp(name, "jit_max_regs"))
+        c->jit_max_regs = (int)std::max<int64_t>(0, std::min<int64_t>(value, 255));
     else if (!strcmp(name, "plan_max"))
         c->plan_max = (int)std::max<int64_t>(1, std::min<int64_t>(value, PLAN_MAX));
     else if (!strcmp(name, "jit_log1p")) {

@@ -36,7 +36,8 @@ struct JitKernel {
 // Compiles `src` for sm_100a with NVRTC.  Returns false (and a message in `err`) when NVRTC is unavailable or the
 // compilation fails.  `cubin` receives the binary; no GPU is needed.
 // min_blocks: __launch_bounds__(32, min_blocks) — caps the registers so that that many warps fit per SM
-bool jit_compile(const std::string &src, std::string &cubin, std::string &err, int min_blocks = 1);
+// max_regs > 0: __maxnreg__(max_regs) instead of the min_blocks bound
+bool jit_compile(const std::string &src, std::string &cubin, std::string &err, int min_blocks = 1, int max_regs = 0);
 
 // Loads a cubin into the current CUDA context (driver API through dlopen) and looks up `ftsb_jit`.
 bool jit_load(const std::string &cubin, int smem_bytes, JitKernel &out, std::string &err);
