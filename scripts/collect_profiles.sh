@@ -1,9 +1,9 @@
 #!/bin/bash
 # Collects the bench lines and ncu captures committed under profiles/ (run under gpurun; writes gpurun_out/).
-# usage: scripts/collect_profiles.sh [tag]   (tag names the files: r01b -> gpurun_out/r01b_*.json ...)
+# usage: scripts/collect_profiles.sh [tag]   (tag names the files: r01c -> gpurun_out/r01c_*.json ...)
 cd "$(dirname "$0")/.."
 O=gpurun_out
-T=${1:-r01b}
+T=${1:-r01c}
 python bench.py > $O/${T}_bench_c2.json 2> $O/${T}_bench_c2.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_c2_reference.json 2>> $O/${T}_bench_c2.err
 python bench.py --workload c3 --steps 5 --no-cpu > $O/${T}_bench_c3.json 2> $O/${T}_bench_c3.err
