@@ -81,6 +81,8 @@ struct ftsb_circuit {
     int jit_occ[2] = {0, 0};
     int jit_opt = 1;
     int jit_log1p = 1;      // 1: generated kernels use fts_log1p.h like the built kernels; 0: CUDA's log1p (A/B measurements)
+    int jit_two_pass = 8;   // k > 0: .op of nonlinear circuits in passes of k Newton iterations (launch_jit)
+    int jit_passes = 2;     // number of passes (the last one runs to the end)
     int jit_max_regs = 0;   // > 0: __maxnreg__ of the generated kernel (instead of jit_min_blocks).  Measured: 224 / 216 registers
                             // still give 2 warps per scheduler (16 K registers each): a third needs <= 168 and spills
     int jit_min_blocks = 1; // __launch_bounds__(32, this): register cap of the generated kernel
@@ -106,7 +108,8 @@ struct ftsb_circuit {
     bool pipe_ready = false;
     int pipe_chunks = 4; // chunks per call (option "pipe_chunks"; 1 = serial copies)
     DevBuf pipe_work;
-    unsigned long long pipe_begin[PIPE_MAX] = {};
+    static constexpr int PASS_MAX = 8;
+    unsigned long long pipe_begin[PASS_MAX * PIPE_MAX] = {};
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
                            // 2-3 warps per SM in shared memory and is latency bound)
@@ -655,14 +658,14 @@ bool ensure_jit(ftsb_circuit *c, int an)
 // global instance indices and the kernel's batch bound is `end`, so several ranges can be in flight on different
 // streams with one shared redo list and one set of counters.
 int launch_jit_range(ftsb_circuit *c, int an, RunArgs &a, cudaStream_t stream, unsigned long long *work, long long begin,
-                     long long end)
+                     long long end, int stop_it = 0, int resume = 0)
 {
     const std::vector<int> &ib = c->comp.ints();
     int sweep_slot = an == AN_DC ? ib[c->comp.off_src + 5 * a.sweep_src + 1] : 0;
     const double *vals = a.vals, *fn = a.fn, *st = a.start, *sp = a.stop, *se = a.step;
     long long batch = end, max_points = a.max_points;
     void *params[] = {&vals, &fn, &batch, &work, &a.counters, &a.x, &a.n_iters, &a.status, &a.redo_list, &a.redo_count,
-                      &st, &sp, &se, &max_points, &a.points_done, &sweep_slot};
+                      &st, &sp, &se, &max_points, &a.points_done, &sweep_slot, &stop_it, &resume};
     // every resident slot: lanes refill as their instances finish, so 65 536 instances on 37 888 lanes take 1.73 instance times
     // (a grid of 1 024 warps = two whole rounds per lane measured 0.82 ms against 0.705 ms)
     const int grid = (int)std::max(1LL, std::min((end - begin + 31) / 32, (long long)c->jit_occ[an] * c->sm_count));
@@ -672,10 +675,27 @@ int launch_jit_range(ftsb_circuit *c, int an, RunArgs &a, cudaStream_t stream, u
     return 0;
 }
 
+// Two-pass .op (option jit_two_pass = k > 0, nonlinear circuits): pass A runs Newton iterations 0..k-1 of every instance
+// with all lanes of a warp in the same iteration — the only iterations whose pivot sequences vary, so the sibling-plan
+// bodies run with many lanes instead of dragging a whole warp along for one freshly refilled lane — and pauses the
+// instances (status -1, x and the iteration count in the output arrays); pass B continues them with per-lane refill.
+// Same arithmetic: the continuation re-evaluates the devices at the paused iterate, exactly what the next iteration
+// of a single pass does.
+bool jit_two_pass_applies(const ftsb_circuit *c, int an)
+{
+    return c->jit_two_pass > 0 && an == AN_OP && c->comp.mode[an].n_nl > 0;
+}
+
 int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
 {
     FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
-    return launch_jit_range(c, an, a, c->stream, a.work, 0, a.batch);
+    if (!jit_two_pass_applies(c, an)) return launch_jit_range(c, an, a, c->stream, a.work, 0, a.batch);
+    for (int j = 0; j < c->jit_passes; ++j) { // pass j: iterations j k .. (j + 1) k - 1, the last pass to the end
+        if (j) FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+        int rc = launch_jit_range(c, an, a, c->stream, a.work, 0, a.batch, j + 1 < c->jit_passes ? (j + 1) * c->jit_two_pass : 0, j > 0);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
@@ -963,6 +983,10 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->slots_global = value ? 1 : 0;
     else if (!strcmp(name, "fill_cap"))
         c->fill_cap = (int)value;
+    else if (!strcmp(name, "jit_two_pass"))
+        c->jit_two_pass = (int)std::max<int64_t>(0, std::min<int64_t>(value, 99));
+    else if (!strcmp(name, "jit_passes"))
+        c->jit_passes = (int)std::max<int64_t>(2, std::min<int64_t>(value, ftsb_circuit::PASS_MAX));
     else if (!strcmp(name, "jit_max_regs"))
         c->jit_max_regs = (int)std::max<int64_t>(0, std::min<int64_t>(value, 255));
     else if (!strcmp(name, "plan_max"))
@@ -1148,7 +1172,7 @@ int pipe_init(ftsb_circuit *c)
         FTSB_CUDA(c, cudaEventCreateWithFlags(&c->pipe_ev[k], cudaEventDisableTiming));
     }
     FTSB_CUDA(c, cudaEventCreateWithFlags(&c->pipe_ev0, cudaEventDisableTiming));
-    FTSB_CUDA(c, c->pipe_work.ensure(ftsb_circuit::PIPE_MAX * 8));
+    FTSB_CUDA(c, c->pipe_work.ensure(ftsb_circuit::PASS_MAX * ftsb_circuit::PIPE_MAX * 8));
     c->pipe_ready = true;
     return 0;
 }
@@ -1213,9 +1237,10 @@ int solve_pipelined(ftsb_circuit *c, int an, long long B, const PipeIo &io, int 
     long long chunk = ((B + K - 1) / K + 31) / 32 * 32;
     chunk = std::max(chunk, 2048LL);
     K = (int)((B + chunk - 1) / chunk);
-    for (int k = 0; k < K; ++k) c->pipe_begin[k] = (unsigned long long)(k * chunk);
+    for (int j = 0; j < ftsb_circuit::PASS_MAX; ++j)
+        for (int k = 0; k < K; ++k) c->pipe_begin[j * ftsb_circuit::PIPE_MAX + k] = (unsigned long long)(k * chunk);
     FTSB_CUDA(c, cudaMemsetAsync(c->counters.p, 0, CN_COUNT * 8, c->stream));
-    FTSB_CUDA(c, cudaMemcpyAsync(c->pipe_work.p, c->pipe_begin, (size_t)K * 8, cudaMemcpyHostToDevice, c->stream));
+    FTSB_CUDA(c, cudaMemcpyAsync(c->pipe_work.p, c->pipe_begin, sizeof c->pipe_begin, cudaMemcpyHostToDevice, c->stream));
     FTSB_CUDA(c, cudaEventRecord(c->pipe_ev0, c->stream));
     auto d2h = [&](cudaStream_t s, long long b0, long long cnt) -> int {
         FTSB_CUDA(c, cudaMemcpyAsync(io.x + b0 * P * n, a.x + b0 * P * n, (size_t)cnt * P * n * 8, cudaMemcpyDeviceToHost, s));
@@ -1240,7 +1265,12 @@ int solve_pipelined(ftsb_circuit *c, int an, long long B, const PipeIo &io, int 
             FTSB_CUDA(c, cudaMemsetAsync(a.n_iters + b0 * P, 0, (size_t)cnt * P * 4, s));
             FTSB_CUDA(c, cudaMemsetAsync(a.x + b0 * P * n, 0, (size_t)cnt * P * n * 8, s));
         }
-        rc = launch_jit_range(c, an, a, s, (unsigned long long *)c->pipe_work.p + k, b0, b1);
+        if (jit_two_pass_applies(c, an)) {
+            for (int j = 0; j < c->jit_passes && !rc; ++j)
+                rc = launch_jit_range(c, an, a, s, (unsigned long long *)c->pipe_work.p + j * ftsb_circuit::PIPE_MAX + k, b0, b1,
+                                      j + 1 < c->jit_passes ? (j + 1) * c->jit_two_pass : 0, j > 0);
+        } else
+            rc = launch_jit_range(c, an, a, s, (unsigned long long *)c->pipe_work.p + k, b0, b1);
         if (rc) return rc;
         rc = d2h(s, b0, cnt);
         if (rc) return rc;

@@ -880,3 +880,31 @@ def test_log1p_device_equals_host_bitwise():
     u = np.concatenate([sample(seed=5), [np.inf, np.nan]])
     assert np.array_equal(log1p_host(u, device=0), log1p_host(u, device=-1), equal_nan=True)
 
+
+
+@pytest.mark.parametrize("which,rel,k", [("proj1_nl", 0.1, 4), ("proj1_nl", 0.45, 3), ("npn_test", 0.3, 5), ("proj2", 0.3, 1)])
+def test_two_pass_op_equals_single_pass_bitwise(which, rel, k):
+    """Option jit_two_pass = k: the generated .op kernel pauses every instance after Newton iteration k (all lanes of a
+    warp in step through the iterations whose pivot sequences vary) and a second launch continues them.  Outputs and
+    counters must equal the single-pass run's, through the device-buffer path and through the chunk pipeline."""
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else load(which)
+    B = 6000
+    vals, fns = nl.monte_carlo(circ, B, rel=rel)
+    if rel > 0.4:
+        vals[::41, int(np.flatnonzero(np.asarray(circ.kind) == nl.R)[0])] = 0.0  # redo instances
+    ref = BatchEngine(circ)
+    ref.set_params(vals, fns)
+    r0 = ref.run_op()
+    r0 = ref.run_op()
+    c0 = ref.counters()
+    assert ref.variant.startswith("jit"), ref.variant
+    be = BatchEngine(circ)
+    be.set_option("jit_two_pass", k)
+    for i in range(5):
+        r = be.solve_op(vals, fns) if i >= 2 else (be.set_params(vals, fns), be.run_op())[1]
+        c = be.counters()
+        assert np.array_equal(r.x, r0.x, equal_nan=True) and np.array_equal(r.n_iters, r0.n_iters)
+        assert np.array_equal(r.status, r0.status)
+        for key in ("solve_points", "newton_iters", "lu_factor", "lu_solve"):
+            assert c[key] == c0[key], (key, c, c0, be.variant)
+    assert "/pipe" in be.variant, be.variant
