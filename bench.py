@@ -486,7 +486,11 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
                          "kernel": f"{kname}<{wl['kind']}> ({dev_variant})",
-                         "kernel_ms": kern_ms, "executed_flops_per_launch": exec_flops,
+                         "kernel_ms": kern_ms, "launches_per_step": launches / max(args.steps, 1),
+                         "note": "per step = per batch: the .op step of a nonlinear small circuit is two launches of the same "
+                                 "generated kernel (pass A: iterations 0..7, pass B: the rest) + the dense redo pass; flops and "
+                                 "kernel_ms cover the whole step, profiles/traffic.json holds the ncu figures of pass B",
+                         "executed_flops_per_launch": exec_flops,
                          "reference_equivalent_flops_per_launch": ref_flops,
                          "peak_source": "DFMA micro-benchmark in this run (ftsb_measure_fp64_tflops); MEASURED_PEAKS.json has no "
                                         "fp64 entry. The solution path runs without FMA contraction (parity), so DMUL+DADD pairs "
