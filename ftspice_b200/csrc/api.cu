@@ -83,6 +83,7 @@ struct ftsb_circuit {
     int jit_log1p = 1;      // 1: generated kernels use fts_log1p.h like the built kernels; 0: CUDA's log1p (A/B measurements)
     int jit_two_pass = 8;   // k > 0: .op of nonlinear circuits in passes of k Newton iterations (launch_jit)
     int jit_passes = 2;     // number of passes (the last one runs to the end)
+    int jit_two_pass_min_plans = 3; // ... for circuits whose pivot sequences needed at least this many plans
     int jit_max_regs = 0;   // > 0: __maxnreg__ of the generated kernel (instead of jit_min_blocks).  Measured: 224 / 216 registers
                             // still give 2 warps per scheduler (16 K registers each): a third needs <= 168 and spills
     int jit_min_blocks = 1; // __launch_bounds__(32, this): register cap of the generated kernel
@@ -683,7 +684,8 @@ int launch_jit_range(ftsb_circuit *c, int an, RunArgs &a, cudaStream_t stream, u
 // of a single pass does.
 bool jit_two_pass_applies(const ftsb_circuit *c, int an)
 {
-    return c->jit_two_pass > 0 && an == AN_OP && c->comp.mode[an].n_nl > 0;
+    // worth a second launch only when several plans are live (measured: K = 6 -21 %, K = 4 -4 %, K <= 2 +2..10 %)
+    return c->jit_two_pass > 0 && an == AN_OP && c->comp.mode[an].n_nl > 0 && c->plan_host[an].K >= c->jit_two_pass_min_plans;
 }
 
 int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
@@ -985,6 +987,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->fill_cap = (int)value;
     else if (!strcmp(name, "jit_two_pass"))
         c->jit_two_pass = (int)std::max<int64_t>(0, std::min<int64_t>(value, 99));
+    else if (!strcmp(name, "jit_two_pass_min_plans"))
+        c->jit_two_pass_min_plans = (int)std::max<int64_t>(1, value);
     else if (!strcmp(name, "jit_passes"))
         c->jit_passes = (int)std::max<int64_t>(2, std::min<int64_t>(value, ftsb_circuit::PASS_MAX));
     else if (!strcmp(name, "jit_max_regs"))

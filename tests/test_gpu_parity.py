@@ -900,6 +900,7 @@ def test_two_pass_op_equals_single_pass_bitwise(which, rel, k):
     assert ref.variant.startswith("jit"), ref.variant
     be = BatchEngine(circ)
     be.set_option("jit_two_pass", k)
+    be.set_option("jit_two_pass_min_plans", 1)  # also for circuits with one or two plans (off by default there: no gain)
     for i in range(5):
         r = be.solve_op(vals, fns) if i >= 2 else (be.set_params(vals, fns), be.run_op())[1]
         c = be.counters()
