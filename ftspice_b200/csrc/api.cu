@@ -17,6 +17,7 @@
 #include "solver_lanes.cuh"
 #include "solver_plan.cuh"
 #include "solver_sparse.cuh"
+#include "solver_team.cuh"
 #include "solver_warp.cuh"
 
 using namespace ftsb;
@@ -111,6 +112,13 @@ struct ftsb_circuit {
     DevBuf pipe_work;
     static constexpr int PASS_MAX = 8;
     unsigned long long pipe_begin[PASS_MAX * PIPE_MAX] = {};
+    // per-team .tran kernels for n > 16 (solver_team.cuh): static elimination plan along the predicted pivot sequence
+    TeamPlanHost team_plan;
+    DevBuf team_buf, team_scratch, redo2;
+    int team_state = 0;    // 0 = not tried, 1 = plan on the device, -1 = no usable plan
+    int team_opt = 1;      // option "team": 1 (default) use them, 0 = the warp-per-instance kernels as before
+    int team_g = 0;        // option "team_lanes": lanes per instance (0 = automatic)
+    int team_place = -1;   // option "team_place": bit 0 slot table, bit 1 factors in shared memory (-1 = automatic)
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
                            // 2-3 warps per SM in shared memory and is latency bound)
@@ -562,6 +570,7 @@ int relearn_plans(ftsb_circuit *c, int an)
         return 0;
     }
     (void)k_before; // new plans (or a new order): the specialised kernel is regenerated on demand
+    FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
     jit_unload(c->jit[an]);
     c->jit_state[an] = 0;
     return 0;
@@ -700,6 +709,104 @@ int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
     return 0;
 }
 
+// ---- per-team .tran kernels (solver_team.cuh) ----------------------------------------------------------------
+struct TeamLaunch {
+    TeamKernelFn fn = nullptr;
+    int g = 0, place = 0, grid = 1;
+    size_t smem = 0, scratch_bytes = 0;
+    TeamArgs ta{};
+};
+
+// Returns 0 when the per-team kernel was chosen for this .tran run.
+int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
+{
+    if (an != AN_TRAN || !c->team_opt || !c->sparse_warp || !c->skip_refactor || c->force_generic || c->force_cta) return 1;
+    if (std::max(c->comp.n_start, 1) <= 16) return 1;
+    const ModeOff &mo = c->comp.mode[an];
+    if (mo.n < 1 || !mo.sp.piv_valid) return 1;
+    if (c->team_state == 0) {
+        c->team_state = -1;
+        const std::vector<int> &ib = c->comp.ints();
+        std::vector<int> piv(ib.begin() + mo.sp.piv, ib.begin() + mo.sp.piv + mo.n);
+        if (!build_team_plan(c->comp, an, piv, c->team_plan)) return 1;
+        const TeamPlanHost &ph = c->team_plan;
+        if (c->team_buf.ensure(ph.ibuf.size() * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (cudaMemcpyAsync(c->team_buf.p, ph.ibuf.data(), ph.ibuf.size() * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        c->team_state = 1;
+    }
+    if (c->team_state != 1) return 1;
+    const TeamPlanHost &ph = c->team_plan;
+    const bool linear = mo.n_nl == 0;
+    const int place = c->team_place >= 0 ? (c->team_place & 3) : (linear ? 0 : 3);
+    // lanes per instance: rows are dealt round-robin, so few lanes waste little; more teams per warp amortise the
+    // list-walking code over more instances but need more shared memory per warp
+    int best_g = 0, best_occ = 0;
+    size_t best_smem = 0;
+    TeamLayout best_lay{};
+    for (int g : {8, 16, 32}) {
+        if (c->team_g > 0) g = c->team_g;
+        TeamKernelFn fn = team_kernel(g, place);
+        if (fn) {
+            const int T = 32 / g;
+            const TeamLayout lay = team_layout(mo.n, ph.nA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place);
+            const size_t smem = (size_t)2 * FTS_LOG1P_N * 8 + (size_t)TEAM_WARPS * lay.sm_doubles * T * 8;
+            int occ = 0;
+            if (smem <= c->smem_optin &&
+                cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32 * TEAM_WARPS, smem) == cudaSuccess && occ >= 1) {
+                // automatic: the smallest lane count that keeps two warps per scheduler resident; a circuit too large for
+                // that (n = 258: 50 KB per instance) stays with the warp kernel and its global scratch rows
+                if (c->team_g > 0 || occ * TEAM_WARPS >= 8) {
+                    best_g = g;
+                    best_occ = occ;
+                    best_smem = smem;
+                    best_lay = lay;
+                }
+            } else
+                cudaGetLastError();
+        }
+        if (c->team_g > 0 || best_g) break;
+    }
+    if (!best_g) return 1;
+    const int T = 32 / best_g;
+    tl.fn = team_kernel(best_g, place);
+    tl.g = best_g;
+    tl.place = place;
+    tl.smem = best_smem;
+    const long long per_block = (long long)TEAM_WARPS * T;
+    tl.grid = (int)std::max(1LL, std::min((batch + per_block - 1) / per_block, (long long)best_occ * c->sm_count));
+    tl.scratch_bytes = (size_t)tl.grid * TEAM_WARPS * best_lay.gl_doubles * T * 8;
+    tl.ta.plan = ph.view((const int *)c->team_buf.p);
+    tl.ta.lay = best_lay;
+    tl.ta.flops_factor = ph.flops_factor;
+    tl.ta.flops_solve = ph.flops_solve;
+    if (cudaFuncSetAttribute((const void *)tl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    c->variant = "team" + std::to_string(best_g) + "p" + std::to_string(place) + "_n" + std::to_string(mo.n) + "/A" + std::to_string(ph.nA) +
+                 "/S" + std::to_string(ph.S) + "/occ" + std::to_string(best_occ * TEAM_WARPS);
+    return 0;
+}
+
+int launch_team(ftsb_circuit *c, TeamLaunch &tl, RunArgs &a)
+{
+    FTSB_CUDA(c, c->team_scratch.ensure(tl.scratch_bytes));
+    tl.ta.gscratch = (double *)c->team_scratch.p;
+    FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
+    void *args[] = {&a, &tl.ta};
+    FTSB_CUDA(c, cudaLaunchKernel((const void *)tl.fn, dim3(tl.grid), dim3(32 * TEAM_WARPS), args, tl.smem, c->stream));
+    c->launches++;
+    return 0;
+}
+
 // one analysis over the batch: the sparse kernel followed by the dense kernels on the instances it abandoned, or
 // the dense / small-circuit kernels alone.  `dense_lanes`: the dense plan takes an external start-up solution.
 int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
@@ -733,6 +840,22 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         if (need) FTSB_CUDA(c, c->scratch.ensure(need));
     }
     a.scratch = (double *)c->scratch.p;
+    std::string tv;
+    if (sparse && !planned) { // .tran, n > 16: the per-team kernel first; what leaves its plan goes down the chain below
+        TeamLaunch tl;
+        if (plan_team(c, an, a.batch, tl) == 0) {
+            tv = c->variant;
+            FTSB_CUDA(c, c->redo2.ensure((size_t)a.batch * 8));
+            RunArgs at = a;
+            at.redo_list = (long long *)c->redo2.p;
+            at.redo_count = (unsigned long long *)c->counters.p + CN_REDO2;
+            FTSB_CUDA(c, cudaMemsetAsync(at.redo_count, 0, 8, c->stream));
+            rc = launch_team(c, tl, at);
+            if (rc) return rc;
+            a.in_list = at.redo_list;
+            a.in_count = at.redo_count;
+        }
+    }
     if (sparse) {
         FTSB_CUDA(c, c->redo.ensure((size_t)a.batch * 8));
         RunArgs as = a;
@@ -745,6 +868,8 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         as.redo_list = (long long *)c->redo.p;
         as.redo_count = (unsigned long long *)c->counters.p + CN_REDO;
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
+        if (c->last_redo_an >= 0 && c->last_redo_an != an && c->last_redo_an < 2)
+            c->redo_traced[c->last_redo_an] = false; // its redo count is gone: do not relearn from a stale counter
         rc = use_jit ? launch_jit(c, an, as) : launch_kernel(c, ps, as);
         if (rc) return rc;
         a.in_list = as.redo_list;
@@ -761,6 +886,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
     rc = launch_kernel(c, pd, a);
     if (rc) return rc;
     variant = sparse ? sv + "+redo:" + dv : dv;
+    if (!tv.empty()) variant = tv + "+redo:" + variant;
     return 0;
 }
 
@@ -826,6 +952,17 @@ __global__ void k_transpose(const double *__restrict__ in, double *__restrict__ 
     for (int j = threadIdx.y; j < 32; j += 8) {
         long long cc = c0 + j, r = r0 + threadIdx.x;
         if (r < rows && cc < cols) out[cc * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+// the generated kernels depend on an option that changed: wait for work in flight (an asynchronous FTSB_MEM_DEVICE run may
+// still execute the module), unload, regenerate on demand
+void jit_reset(ftsb_circuit *c)
+{
+    if (cudaSetDevice(c->device) == cudaSuccess && c->stream) cudaStreamSynchronize(c->stream);
+    for (int an = 0; an < 2; ++an) {
+        jit_unload(c->jit[an]);
+        c->jit_state[an] = 0;
     }
 }
 
@@ -942,7 +1079,8 @@ void ftsb_destroy(ftsb_circuit *c)
     c->pipe_work.release();
     DevBuf *bufs[] = {&c->ibuf, &c->vals, &c->fn, &c->tmp_in, &c->work, &c->counters, &c->scratch, &c->o_x, &c->o_it,
                       &c->o_status, &c->o_done, &c->o_t, &c->o_nrec, &c->o_xf, &c->i_start, &c->i_stop, &c->i_step, &c->s_x, &c->s_it,
-                      &c->s_st, &c->redo, &c->plan_buf[0], &c->plan_buf[1], &c->trace};
+                      &c->s_st, &c->redo, &c->plan_buf[0], &c->plan_buf[1], &c->trace, &c->team_buf, &c->team_scratch,
+                      &c->redo2};
     for (DevBuf *b : bufs) b->release();
     jit_unload(c->jit[0]);
     jit_unload(c->jit[1]);
@@ -973,10 +1111,18 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->plan_lanes = (int)value;
     else if (!strcmp(name, "jit"))
         c->jit_opt = value ? 1 : 0;
-    else if (!strcmp(name, "jit_min_blocks"))
+    else if (!strcmp(name, "jit_min_blocks")) {
         c->jit_min_blocks = (int)value;
+        jit_reset(c);
+    }
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "team"))
+        c->team_opt = value ? 1 : 0;
+    else if (!strcmp(name, "team_lanes"))
+        c->team_g = (int)value;
+    else if (!strcmp(name, "team_place"))
+        c->team_place = (int)value;
     else if (!strcmp(name, "hist_global"))
         c->hist_global_opt = value ? 1 : 0;
     else if (!strcmp(name, "windowed"))
@@ -991,16 +1137,15 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->jit_two_pass_min_plans = (int)std::max<int64_t>(1, value);
     else if (!strcmp(name, "jit_passes"))
         c->jit_passes = (int)std::max<int64_t>(2, std::min<int64_t>(value, ftsb_circuit::PASS_MAX));
-    else if (!strcmp(name, "jit_max_regs"))
+    else if (!strcmp(name, "jit_max_regs")) {
         c->jit_max_regs = (int)std::max<int64_t>(0, std::min<int64_t>(value, 255));
+        jit_reset(c);
+    }
     else if (!strcmp(name, "plan_max"))
         c->plan_max = (int)std::max<int64_t>(1, std::min<int64_t>(value, PLAN_MAX));
     else if (!strcmp(name, "jit_log1p")) {
         c->jit_log1p = (int)std::max<int64_t>(0, std::min<int64_t>(value, 3));
-        for (int an = 0; an < 2; ++an) { // regenerate on demand
-            jit_unload(c->jit[an]);
-            c->jit_state[an] = 0;
-        }
+        jit_reset(c);
     } else if (!strcmp(name, "pipe_chunks"))
         c->pipe_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(value, ftsb_circuit::PIPE_MAX));
     else
@@ -1189,7 +1334,27 @@ struct PipeIo { // host buffers of one call
     long long P; // points per instance (.op: 1)
 };
 
+// an error path of the pipelined call must not return while chunk streams still copy into the caller's buffers
+void pipe_drain(ftsb_circuit *c)
+{
+    const std::string keep = c->err;
+    if (c->pipe_ready)
+        for (int k = 0; k < ftsb_circuit::PIPE_MAX; ++k) cudaStreamSynchronize(c->pipe[k]);
+    cudaStreamSynchronize(c->stream);
+    cudaGetLastError();
+    c->err = keep;
+}
+
+int solve_pipelined_impl(ftsb_circuit *c, int an, long long B, const PipeIo &io, int sweep_src);
+
 int solve_pipelined(ftsb_circuit *c, int an, long long B, const PipeIo &io, int sweep_src)
+{
+    const int rc = solve_pipelined_impl(c, an, B, io, sweep_src);
+    if (rc) pipe_drain(c);
+    return rc;
+}
+
+int solve_pipelined_impl(ftsb_circuit *c, int an, long long B, const PipeIo &io, int sweep_src)
 {
     int rc = pipe_init(c);
     if (rc) return rc;
@@ -1687,5 +1852,33 @@ extern "C" int ftsb_debug_jit(const ftsb_elem *elems, int32_t n_elems, int32_t n
         }
     }
     say("ok K=" + std::to_string(ph.K) + " S=" + std::to_string(ph.S) + " cubin " + std::to_string(cubin.size()) + " bytes; " + err);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// diagnostics (not part of include/ftsb.h): the static elimination plan of the per-team kernels, built without a GPU.
+// meta[0..6] = n, nA, S, nJ, nT, nU, nB; meta[7..23] = the 17 list offsets in TeamPlanHost order; meta[24] = ints used.
+// jdst[nJ] = row | col << 16 of the static entries, piv[n] = the pivot sequence the plan follows.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t n_start, const int32_t *row_class,
+                                    int32_t an, int32_t *ibuf, int32_t cap, int32_t *meta, int32_t *jdst, int32_t *piv)
+{
+    Compiled comp;
+    std::string err;
+    if (!compile_circuit(reinterpret_cast<const ElemDesc *>(elems), n_elems, n_run, n_start, row_class, 0, comp, err)) return -1;
+    const ModeOff &mo = comp.mode[an];
+    if (!mo.sp.piv_valid) return -2;
+    const std::vector<int> &ib = comp.ints();
+    std::vector<int> pv(ib.begin() + mo.sp.piv, ib.begin() + mo.sp.piv + mo.n);
+    TeamPlanHost ph;
+    if (!build_team_plan(comp, an, pv, ph)) return -3;
+    if ((int)ph.ibuf.size() > cap) return -4;
+    std::copy(ph.ibuf.begin(), ph.ibuf.end(), ibuf);
+    const int m[] = {ph.n, ph.nA, ph.S, ph.nJ, ph.nT, ph.nU, ph.nB, ph.o_arow, ph.o_acol, ph.o_aptr, ph.o_acon, ph.o_sptr, ph.o_scon,
+                     ph.o_pivrow, ph.o_pive, ph.o_tptr, ph.o_tgt, ph.o_tgtr, ph.o_uptr, ph.o_updm, ph.o_updds, ph.o_bptr, ph.o_bwde,
+                     ph.o_bwdr, (int)ph.ibuf.size()};
+    std::copy(m, m + 25, meta);
+    for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
+    std::copy(pv.begin(), pv.end(), piv);
     return 0;
 }

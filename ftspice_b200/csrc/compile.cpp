@@ -380,6 +380,7 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
             std::vector<int> pos(std::max(n, 1)), piv(std::max(n, 1));
             std::vector<char> noswap(std::max(n, 1), 0);
             for (int i = 0; i < n; ++i) pos[i] = piv[i] = i;
+            bool piv_valid = n > 0;
             for (int k = 0; k < n; ++k) {
                 int P = -1, bestpos = 1 << 30;
                 bool bestunit = false;
@@ -396,7 +397,10 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
                         bestunit = unit;
                     }
                 }
-                if (P < 0) continue; // structurally singular column: nothing to predict
+                if (P < 0) { // structurally singular column: nothing to predict
+                    piv_valid = false;
+                    continue;
+                }
                 const int rk = piv[k], pp = pos[P];
                 noswap[k] = pp == k;
                 piv[k] = P;
@@ -468,6 +472,8 @@ bool compile_circuit(const ElemDesc *elems, int n_elems, int n_run, int n_start,
             }
             o.sp.nnz = (int)erow.size();
             o.sp.n_pred = n_pred;
+            o.sp.piv = im.push(piv);
+            o.sp.piv_valid = piv_valid ? 1 : 0;
             o.sp.cptr = im.push(cptr);
             o.sp.erow = im.push(erow);
             o.sp.rptr = im.push(rptr);

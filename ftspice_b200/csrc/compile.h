@@ -21,6 +21,8 @@ struct GatherOff {
 
 struct SparseOff {
     int nnz = 0, n_pred = 0, cptr = 0, erow = 0, rptr = 0, rcol = 0, rent = 0, n_long = 0, rlong = 0, lmap = 0, window_hint = 0;
+    int piv = 0;       // [n] predicted pivot row of every elimination step (the guess the static structure was built with)
+    int piv_valid = 0; // every column had a structural pivot candidate
     GatherOff S;
 };
 

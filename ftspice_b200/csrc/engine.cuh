@@ -34,7 +34,7 @@ __device__ __forceinline__ double damp_log1p(double u) { return fts_log1p_pos(u,
 // CN_FLOPS: floating-point operations the structure-exploiting solver executed in factorisations and substitutions
 // (the dense kernels' flops follow from CN_FACTOR / CN_SOLVE and n)
 enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_NEWTON = 4, CN_REJ_PLTE = 5, CN_FLOPS = 6, CN_LOCAL = 7,
-             CN_REDO = 7, CN_WHY = 8, CN_COUNT = 12 };
+             CN_REDO = 7, CN_WHY = 8, CN_REDO2 = 9, CN_COUNT = 12 };
 
 struct RunArgs {
     DevProg prog;
@@ -435,7 +435,7 @@ __device__ __forceinline__ void resid_norms(const Team &tm, const ModeProg &M, c
     double sv = 0.0, si = 0.0;
     for (int i = tm.rank; i < n; i += tm.size()) {
         double ax = 0.0;
-        for (int j = 0; j < n; ++j) ax = fma(w.A[j * ld + i], x[j], ax); // decision-only sum: FMA allowed
+        for (int j = 0; j < n; ++j) ax = ax + w.A[j * ld + i] * x[j]; // separate multiply and add, like the reference's dot (mna.rs:28)
         double hg = 0.0;
         if (M.n_gfun > 0) {
             int own_bad = 0;

@@ -405,7 +405,7 @@ struct LaneSolver {
                     const unsigned wd = (unsigned)__ldg(&M.Ax.con[c]);
                     const double v = w.val[wd & AX_SLOT_MASK];
                     const double xc = x[(wd & ~CON_NEG) >> AX_COL_SHIFT];
-                    ax = fma((wd & CON_NEG) ? -v : v, xc, ax); // decision-only sum: FMA allowed
+                    ax = ax + ((wd & CON_NEG) ? -v : v) * xc; // separate multiply and add, like the reference's dot (mna.rs:28)
                 }
             }
             double hg = 0.0;

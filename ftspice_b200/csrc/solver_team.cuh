@@ -1,0 +1,672 @@
+// solver_team.cuh — .tran for mid-size circuits (n > 16): G lanes per instance, 32 / G instances per warp in lock step.
+//
+// Why another family.  ncu on the warp-per-instance kernel (solver_sparse.cuh) at the named C4 size (64-node ladder,
+// n = 65, linear) shows ~21 000 warp instructions per accepted step for what is, per step, one pair of sparse
+// substitutions and ~13 damped updates of 65 unknowns with a 192-term residual: 86 % of the instructions walk maps,
+// shuffle five-level butterflies for 65-element norms and run 65-row loops three lanes-rounds deep with the third round
+// 1/32 full.  Here:
+//   * a TEAM of G lanes (4 / 8 / 16 / 32) owns an instance; rows, devices and companion elements are dealt to the
+//     lanes round-robin (n = 65 on 8 lanes: 9 rounds, 90 % full), norms need log2(G) shuffle levels;
+//   * the 32 / G teams of a warp run in lock step at the level of a transient ATTEMPT (transient.rs:35-91): every team
+//     builds its own right-hand side at its own t + h, all solve, all iterate Newton until the slowest has converged,
+//     every team accepts / rejects on its own (PLTE, h control, state update) and a team whose instance is finished
+//     fetches the next one — so the teams' data sit side by side in shared memory ([index][team]: conflict free) and a
+//     step of the list-walking code serves 32 / G instances;
+//   * the elimination follows a static plan (team_plan.h): pivot sequence fixed, fill-in / targets / updates /
+//     substitution lists worked out on the host, the reference's pivot rule CHECKED at every step; an instance that
+//     leaves the plan goes to the warp kernel (dynamic pivoting) and from there to the dense kernels;
+//   * the residual uses the ASSEMBLED entries of A (sum of the stamps in the reference's order, then a(r,c) * x(c) with a
+//     separate multiply and add, mna.rs:28) instead of one multiply-add per stamp term;
+//   * what is touched once per accepted step — C/L state, the ring of the last three accepted x, for linear circuits
+//     also the slot table and the factors — lives in a per-warp global scratch region with the same [index][team]
+//     layout (coalesced, L2 resident): 3.6 KB of shared memory per instance at n = 65.
+// The solution-path arithmetic (assembly order, pivot rule, reciprocal scaling, separate multiply / subtract, damping,
+// state update, PLTE) is the one of the other families, operation for operation: outputs compare equal bit for bit
+// (tests/test_gpu_parity.py).  Reference: transient.rs:18-105, newtons_method.rs:19-89, gauss_lu.rs:3-54,
+// state_history.rs:40-56, engine.rs:142-206.
+#pragma once
+#include "solver_sparse.cuh"
+#include "team_plan.h"
+
+namespace ftsb {
+
+// offsets in doubles per team; an array lives in shared memory or in the warp's global region ("g" offsets)
+struct TeamLayout {
+    int ox, oxp, ob, oy, oA, oprev;      // shared
+    int oval, osv, oalpha;               // shared (PLACE bits 0 / 1) or global
+    int ostate, oring, odynv;            // global
+    int sm_doubles, gl_doubles;
+};
+
+// place: bit 0 = slot table in shared memory, bit 1 = factors in shared memory (nonlinear circuits: both are touched in
+// every Newton iteration)
+__host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_slots, int n_dyn, int n_src, int place)
+{
+    TeamLayout t;
+    int so = 0, go = 0;
+    auto ts = [&](int c) {
+        int r = so;
+        so += c;
+        return r;
+    };
+    auto tg = [&](int c) {
+        int r = go;
+        go += c;
+        return r;
+    };
+    t.ox = ts(n);
+    t.oxp = ts(n);
+    t.ob = ts(n);
+    t.oy = ts(n);
+    t.oA = ts(nA);
+    t.oprev = ts(3 * n_src);
+    t.oval = (place & 1) ? ts(n_slots) : tg(n_slots);
+    t.osv = (place & 2) ? ts(S) : tg(S);
+    t.oalpha = (place & 2) ? ts(n) : tg(n);
+    t.ostate = tg(2 * n_dyn);
+    t.oring = tg(3 * n);
+    t.odynv = tg(n_dyn);
+    t.sm_doubles = so;
+    t.gl_doubles = go > 0 ? go : 1;
+    return t;
+}
+
+struct TeamArgs {
+    TeamPlan plan;
+    TeamLayout lay;
+    double *gscratch; // [grid * warps per block][gl_doubles][T]
+    long long flops_factor, flops_solve;
+};
+
+constexpr int TEAM_WARPS = 4; // warps per block (they share the ln_1p table)
+
+template <int G>
+struct TeamOps {
+    static constexpr int T = 32 / G;
+    using V = Vec<T>;
+
+    static __device__ __forceinline__ void sum2(double &a, double &b)
+    {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+    }
+    static __device__ __forceinline__ int sumi(int v)
+    {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ bool any(bool p, unsigned tmask) { return (__ballot_sync(0xffffffffu, p) & tmask) != 0u; }
+
+    // row-indexed gather: out[row] = sum of +-val[slot] (reference accumulation order)
+    static __device__ __forceinline__ double gsum(const Gather &g, int row, V val, double acc)
+    {
+        const int c0 = __ldg(&g.ptr[row]), c1 = __ldg(&g.ptr[row + 1]);
+        for (int c = c0; c < c1; ++c) {
+            const unsigned wd = (unsigned)__ldg(&g.con[c]);
+            const double v = val[wd & ~CON_NEG];
+            acc += (wd & CON_NEG) ? -v : v;
+        }
+        return acc;
+    }
+
+    // entries of A and of J from the slot table (fill-in entries of the plan start at 0.0)
+    static __device__ __forceinline__ void assemble(const TeamPlan &P, V val, V A, V sv, int l, bool on)
+    {
+        if (on) {
+            for (int e = l; e < P.nA; e += G) {
+                double acc = 0.0;
+                const int c0 = __ldg(&P.aptr[e]), c1 = __ldg(&P.aptr[e + 1]);
+                for (int c = c0; c < c1; ++c) {
+                    const unsigned wd = (unsigned)__ldg(&P.acon[c]);
+                    const double v = val[wd & ~CON_NEG];
+                    acc += (wd & CON_NEG) ? -v : v;
+                }
+                A[e] = acc;
+            }
+        }
+    }
+    static __device__ __forceinline__ void assemble_sv(const TeamPlan &P, V val, V sv, int l, bool on)
+    {
+        if (on) {
+            for (int e = l; e < P.nJ; e += G) {
+                double acc = 0.0;
+                const int c0 = __ldg(&P.sptr[e]), c1 = __ldg(&P.sptr[e + 1]);
+                for (int c = c0; c < c1; ++c) {
+                    const unsigned wd = (unsigned)__ldg(&P.scon[c]);
+                    const double v = val[wd & ~CON_NEG];
+                    acc += (wd & CON_NEG) ? -v : v;
+                }
+                sv[e] = acc;
+            }
+            for (int e = P.nJ + l; e < P.S; e += G) sv[e] = 0.0;
+        }
+    }
+
+    // gauss_lu.rs:3-42 along the plan.  Returns true when the team must leave the plan: the planned row is not the
+    // reference's pivot (first position with the strictly largest |a|), or a candidate is zero-only / infinite / NaN.
+    static __device__ bool factor(const TeamPlan &P, V sv, V alpha, int l, bool on, unsigned tmask)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        bool bad = false;
+        const int n = P.n;
+        int t0 = __ldg(&P.tptr[0]);
+        for (int k = 0; k < n; ++k) {
+            const int t1 = __ldg(&P.tptr[k + 1]);
+            const int eP = __ldg(&P.pive[k]);
+            double ap = 1.0;
+            if (on) ap = sv[eP];
+            const double abs_p = fabs(ap);
+            bad |= !(abs_p > 0.0 && abs_p < INF);
+            const double al = 1.0 / ap; // (:31)
+            for (int tt = t0 + l; tt < t1; tt += G) {
+                const int w = __ldg(&P.tgt[tt]);
+                if (on) {
+                    const int e = w & 0xffff;
+                    const double a = sv[e];
+                    const double av = fabs(a);
+                    bad |= (w >> 30) ? !(av < abs_p) : !(av <= abs_p);
+                    sv[e] = al * a; // (:32)
+                }
+            }
+            if (on && l == 0) alpha[k] = al;
+            if (t1 > t0) {
+                __syncwarp();
+                const int u0 = __ldg(&P.uptr[t0]), u1 = __ldg(&P.uptr[t1]);
+                for (int u = u0 + l; u < u1; u += G) {
+                    const int em = __ldg(&P.updm[u]);
+                    const int ds = __ldg(&P.updds[u]);
+                    if (on) {
+                        const double m = sv[em];
+                        if (m != 0.0) { // a - 0 * p == a
+                            const int d = ds & 0xffff, s = (ds >> 16) & 0xffff;
+                            sv[d] = sv[d] - m * sv[s]; // (:35-39)
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            t0 = t1;
+        }
+        return any(on && bad, tmask);
+    }
+
+    // y through the stored multipliers (gauss_lu.rs:40, in step order)
+    static __device__ void forward(const TeamPlan &P, V sv, V y, int l, bool on)
+    {
+        const int n = P.n;
+        int t0 = __ldg(&P.tptr[0]);
+        for (int k = 0; k < n; ++k) {
+            const int t1 = __ldg(&P.tptr[k + 1]);
+            if (t1 > t0) {
+                const int pk = __ldg(&P.pivrow[k]);
+                for (int tt = t0 + l; tt < t1; tt += G) {
+                    const int e = __ldg(&P.tgt[tt]) & 0xffff, r = __ldg(&P.tgtr[tt]);
+                    if (on) {
+                        const double m = sv[e];
+                        if (m != 0.0) y[r] = y[r] - m * y[pk];
+                    }
+                }
+                __syncwarp();
+            }
+            t0 = t1;
+        }
+    }
+
+    // gauss_lu.rs:44-53; false when a solution component is not finite
+    static __device__ bool backward(const TeamPlan &P, V sv, V alpha, V y, V xp, int l, bool on)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        const int n = P.n;
+        bool ok = true;
+        int b1 = __ldg(&P.bptr[n]);
+        for (int i = n - 1; i >= 0; --i) {
+            const int b0 = __ldg(&P.bptr[i]);
+            const int pi = __ldg(&P.pivrow[i]), eP = __ldg(&P.pive[i]);
+            double xi = 0.0;
+            if (on) {
+                xi = y[pi] / sv[eP];
+                if (l == 0) xp[i] = xi;
+            }
+            ok = ok && (fabs(xi) < INF);
+            if (b1 > b0) {
+                for (int bb = b0 + l; bb < b1; bb += G) {
+                    const int e = __ldg(&P.bwde[bb]), r = __ldg(&P.bwdr[bb]);
+                    if (on) y[r] = y[r] - xi * sv[e];
+                }
+                __syncwarp();
+            }
+            b1 = b0;
+        }
+        return ok;
+    }
+
+    // nonlinear devices at x -> slot values; returns team-wide (#non-finite currents) | panic << 20
+    static __device__ __forceinline__ int eval_nl(const ModeProg &M, V x, V val, int l, bool on)
+    {
+        if (M.n_nl == 0) return 0;
+        int acc = 0;
+        for (int d = l; d < M.n_nl; d += G) {
+            int desc[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) desc[k] = __ldg(&M.nl[d * 5 + k]);
+            if (on) acc += eval_device(desc, x, val);
+        }
+        acc = sumi(acc);
+        __syncwarp();
+        return acc;
+    }
+};
+
+// place: see team_layout
+template <int G, int PLACE>
+__global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_constant__ RunArgs a, const __grid_constant__ TeamArgs ta)
+{
+    using Ops = TeamOps<G>;
+    constexpr int T = Ops::T;
+    using V = Vec<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tab = reinterpret_cast<double *>(smem_raw);
+    {
+        unsigned long long *t_ = reinterpret_cast<unsigned long long *>(smem_raw);
+        for (int i = threadIdx.x; i < 2 * FTS_LOG1P_N; i += blockDim.x) t_[i] = k_log1p_tab[i];
+    }
+    __syncthreads();
+    const DevProg &DP = a.prog;
+    const ModeProg &M = DP.tran;
+    const TeamPlan &P = ta.plan;
+    const TeamLayout &L = ta.lay;
+    const int n = M.n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane / G, l = lane % G;
+    const unsigned tmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
+    double *sw = tab + 2 * FTS_LOG1P_N + (size_t)warp * L.sm_doubles * T + q;
+    double *gw = ta.gscratch + ((size_t)blockIdx.x * TEAM_WARPS + warp) * (size_t)L.gl_doubles * T + q;
+    const V x{sw + L.ox * T}, xp{sw + L.oxp * T}, b{sw + L.ob * T}, y{sw + L.oy * T}, A{sw + L.oA * T}, prev{sw + L.oprev * T};
+    const V val{((PLACE & 1) ? sw : gw) + L.oval * T};
+    const V sv{((PLACE & 2) ? sw : gw) + L.osv * T}, alpha{((PLACE & 2) ? sw : gw) + L.oalpha * T};
+    const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T};
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const bool linear = M.n_nl == 0;
+
+    // per-team state (uniform over the lanes of a team)
+    bool have = false, exhausted = false, new_step = true;
+    long long inst = -1, nrec = 0, stored = 0;
+    int status = ST_OK;
+    double t = 0.0, h = 1e-18, hA = -1.0, h_first = 1e-18, tr0 = 0.0, tr1 = 0.0, tr2 = 0.0;
+    unsigned long long ci[CN_LOCAL], cn[CN_LOCAL]; // the instance in flight / finished instances
+#pragma unroll
+    for (int i = 0; i < CN_LOCAL; ++i) ci[i] = cn[i] = 0;
+    const unsigned long long total = a.in_list ? *a.in_count : (unsigned long long)a.batch;
+
+    for (;;) {
+        // ---------------------------------------------------------------- refill: idle teams fetch an instance
+        {
+            const bool need = !have && !exhausted;
+            const unsigned nb = __ballot_sync(0xffffffffu, need && l == 0);
+            if (nb) {
+                unsigned long long first = 0;
+                if (lane == 0) first = atomicAdd(a.work, (unsigned long long)__popc(nb));
+                first = __shfl_sync(0xffffffffu, first, 0);
+                if (need) {
+                    const unsigned long long idx = first + (unsigned)__popc(nb & ((1u << (q * G)) - 1u));
+                    if (idx >= total)
+                        exhausted = true;
+                    else {
+                        inst = a.in_list ? a.in_list[idx] : (long long)idx;
+                        have = true;
+                    }
+                }
+            }
+            const bool fresh = need && have;
+            if (!__any_sync(0xffffffffu, have)) break;
+            if (__any_sync(0xffffffffu, fresh)) {
+                if (fresh) { // load_instance (engine.cuh) + start-up solution + init_state (cap.rs:38-47, ind.rs:42-49)
+                    const double *vals = a.vals + inst * DP.n_elems;
+                    const double *fn = a.fn + inst * (long long)DP.n_fn * 7;
+                    if (l == 0) val[SLOT_ONE] = 1.0;
+                    for (int i = l; i < DP.n_res; i += G) {
+                        const int e = __ldg(&DP.res[2 * i]), s = __ldg(&DP.res[2 * i + 1]);
+                        val[s] = 1.0 / vals[e];
+                    }
+                    for (int i = l; i < DP.n_src; i += G) {
+                        const int *sd = &DP.src[5 * i];
+                        const int e = __ldg(&sd[0]), s = __ldg(&sd[1]), fk = __ldg(&sd[3]), fs = __ldg(&sd[4]);
+                        const double v = fk != FN_NONE ? spice_fn_eval(fk, fn + fs * 7, 0.0) : vals[e];
+                        val[s] = v;
+                        prev[3 * i] = v;
+                        prev[3 * i + 1] = v;
+                        prev[3 * i + 2] = v;
+                    }
+                    const double *xs = a.x_start + inst * a.n_start;
+                    for (int i = l; i < n; i += G) x[i] = xs[i];
+                    for (int i = l; i < DP.n_dyn; i += G) {
+                        const int *dd = &DP.dyn[6 * i];
+                        const int e = __ldg(&dd[0]), kind = __ldg(&dd[2]), vp = __ldg(&dd[3]), vn = __ldg(&dd[4]), br = __ldg(&dd[5]);
+                        dynv[i] = vals[e];
+                        if (kind == K_C) {
+                            state[2 * i] = (vp >= 0 ? xs[vp] : 0.0) - (vn >= 0 ? xs[vn] : 0.0);
+                            state[2 * i + 1] = 0.0;
+                        } else {
+                            state[2 * i] = 0.0;
+                            state[2 * i + 1] = xs[br];
+                        }
+                    }
+                    const int st0 = a.start_status[inst];
+                    status = st0;
+                    t = 0.0;
+                    h = 1e-18;
+                    hA = -1.0;
+                    tr0 = tr1 = tr2 = 0.0;
+                    nrec = stored = 0;
+                    new_step = true;
+#pragma unroll
+                    for (int i = 0; i < CN_LOCAL; ++i) ci[i] = 0;
+                }
+                __syncwarp();
+            }
+        }
+        bool act = have && status == ST_OK && t < a.t_stop; // this team runs an attempt in this round
+        bool redo = false;
+        int r_newton = 0; // n_iters >= 0, or -status
+
+        if (__any_sync(0xffffffffu, act)) {
+            // ------------------------------------------------------------ attempt prologue (transient.rs:35-46)
+            if (act && new_step) {
+                h_first = h;
+                // companion models at the first attempt's h (cap/model.rs:10-17, ind/model.rs:10-17; quirk Q10)
+                for (int i = l; i < DP.n_dyn; i += G) {
+                    const int *dd = &DP.dyn[6 * i];
+                    const int s = __ldg(&dd[1]), kind = __ldg(&dd[2]);
+                    const double u = state[2 * i], ic = state[2 * i + 1], pv = dynv[i];
+                    if (kind == K_C) {
+                        const double g = 2.0 * pv / h_first;
+                        val[s] = g;
+                        val[s + 1] = -(ic + g * u);
+                    } else {
+                        const double g = h_first / (2.0 * pv);
+                        val[s] = g;
+                        val[s + 1] = ic + g * u;
+                    }
+                }
+            }
+            const double te = t + h;
+            if (act) { // time-varying sources at t + h (transient.rs:36-42); I sources drift (quirk Q9)
+                const double *fn = a.fn + inst * (long long)DP.n_fn * 7;
+                for (int i = l; i < DP.n_src; i += G) {
+                    const int *sd = &DP.src[5 * i];
+                    const int s = __ldg(&sd[1]), kind = __ldg(&sd[2]), fk = __ldg(&sd[3]), fs = __ldg(&sd[4]);
+                    if (fk != FN_NONE) {
+                        const double v = spice_fn_eval(fk, fn + fs * 7, te);
+                        prev[3 * i + 2] = v;
+                        val[s] = kind == K_V ? v : (prev[3 * i] - prev[3 * i + 1]) + v;
+                    }
+                }
+            }
+            __syncwarp();
+            const bool mchg = act && h_first != hA; // the companion conductances changed: A (and, linear, its factors)
+            if (__any_sync(0xffffffffu, mchg)) {
+                Ops::assemble(P, val, A, sv, l, mchg);
+                if (linear) {
+                    Ops::assemble_sv(P, val, sv, l, mchg);
+                    __syncwarp();
+                    if (Ops::factor(P, sv, alpha, l, mchg, tmask)) redo = true;
+                    if (mchg) {
+                        ci[CN_FACTOR]++;
+                        ci[CN_FLOPS] += (unsigned long long)ta.flops_factor;
+                    }
+                }
+                if (mchg) hA = h_first;
+                __syncwarp();
+            }
+            if (act) { // b of this attempt (sources do not change inside a Newton call)
+                for (int i = l; i < n; i += G) {
+                    const double bi = Ops::gsum(M.b_all, i, val, 0.0);
+                    b[i] = bi;
+                    if (linear) y[i] = bi;
+                }
+            }
+            __syncwarp();
+            bool it_on = act && !redo; // still iterating
+            if (linear) { // one pair of substitutions per attempt: J == A, the proposed solution does not move
+                Ops::forward(P, sv, y, l, it_on);
+                if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                if (it_on) {
+                    ci[CN_SOLVE]++;
+                    ci[CN_FLOPS] += (unsigned long long)ta.flops_solve;
+                }
+                it_on = it_on && !redo;
+                __syncwarp();
+            }
+            // ------------------------------------------------------------ Newton (newtons_method.rs:19-71), all teams in rounds
+            int flags = Ops::eval_nl(M, x, val, l, it_on);
+            if (it_on && (flags >> 20)) {
+                redo = true; // NMOS_UNREACHABLE: the warp kernel reproduces the reference's panic from scratch
+                it_on = false;
+            }
+            double sov = INF, soi = INF, eov = INF, eoi = INF, ev = INF, ei = INF, svn = INF, sin_ = INF;
+            int it = 0;
+            for (;;) {
+                if (it_on && !(it < 100 && !(svn < 0.001 * sov + 1e-6 && sin_ < 0.001 * soi + 1e-9 && ev < 0.001 * eov + 1e-6 &&
+                                             ei < 0.001 * eoi + 1e-9))) {
+                    it_on = false;
+                    r_newton = it < 100 ? it : -ST_NOT_CONVERGED;
+                }
+                if (!__any_sync(0xffffffffu, it_on)) break;
+                if (!linear) {
+                    if (it_on)
+                        for (int i = l; i < n; i += G) y[i] = Ops::gsum(M.r_nl, i, val, b[i]);
+                    Ops::assemble_sv(P, val, sv, l, it_on);
+                    __syncwarp();
+                    if (Ops::factor(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                    Ops::forward(P, sv, y, l, it_on);
+                    if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                    if (it_on) {
+                        ci[CN_FACTOR]++;
+                        ci[CN_SOLVE]++;
+                        ci[CN_FLOPS] += (unsigned long long)(ta.flops_factor + ta.flops_solve);
+                    }
+                    if (redo) it_on = false;
+                    __syncwarp();
+                }
+                double qv = 0.0, qi = 0.0;
+                if (it_on) { // damped step (newtons_method.rs:73-77); x is updated in place (x = x_new, :57-59)
+                    for (int i = l; i < n; i += G) {
+                        const double xi = x[i];
+                        const double d = xp[i] - xi;
+                        const double tt = (1.3 / 16.0) * copysign(1.0, d) * fts_log1p_pos(16.0 * fabs(d), tab);
+                        x[i] = xi + tt;
+                        if (__ldg(&M.cls[i]))
+                            qi += tt * tt;
+                        else
+                            qv += tt * tt;
+                    }
+                }
+                Ops::sum2(qv, qi);
+                svn = sqrt(qv) / (double)M.nv;
+                sin_ = sqrt(qi) / (double)M.ni;
+                __syncwarp();
+                flags = Ops::eval_nl(M, x, val, l, it_on);
+                double fv = 0.0, fi = 0.0;
+                if (it_on) { // f = A x + H g - b (mna.rs:25-29) and its class norms (node_vec_norm.rs:12-33)
+                    const int nbad = flags & 0xfffff;
+                    for (int row = l; row < n; row += G) {
+                        double ax = 0.0;
+                        const int c0 = __ldg(&P.arow[row]), c1 = __ldg(&P.arow[row + 1]);
+                        for (int c = c0; c < c1; ++c) ax = ax + A[c] * x[__ldg(&P.acol[c])];
+                        double hg = 0.0;
+                        if (!linear) {
+                            int own_bad = 0;
+                            const int f0 = __ldg(&M.f_nl.ptr[row]), f1 = __ldg(&M.f_nl.ptr[row + 1]);
+                            for (int c = f0; c < f1; ++c) {
+                                const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
+                                const double v = val[wd & ~CON_NEG];
+                                own_bad += isfinite(v) ? 0 : 1;
+                                hg += (wd & CON_NEG) ? -v : v;
+                            }
+                            if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
+                        }
+                        const double f = ax + hg - b[row];
+                        if (__ldg(&M.cls[row]))
+                            fi += f * f;
+                        else
+                            fv += f * f;
+                    }
+                }
+                Ops::sum2(fv, fi);
+                if (it_on) {
+                    ev = sqrt(fv) / (double)M.nv;
+                    ei = sqrt(fi) / (double)M.ni;
+                    if ((flags >> 20) || isinf(ev) || isinf(ei)) { // the reference panics: reproduced from scratch by the warp kernel
+                        redo = true;
+                        it_on = false;
+                    }
+                    ++it;
+                    ci[CN_NEWTON]++;
+                    eov = ev;
+                    eoi = ei;
+                    sov = svn;
+                    soi = sin_;
+                }
+                __syncwarp();
+            }
+            // ------------------------------------------------------------ accept / reject (transient.rs:48-91)
+            bool accepted = false;
+            double next_h = h;
+            int nit = 0;
+            const bool solved = act && !redo;
+            const bool want_plte = solved && r_newton >= 0 && nrec >= 3;
+            double pv = 0.0, pi = 0.0, xv = 0.0, xi2 = 0.0;
+            if (__any_sync(0xffffffffu, want_plte)) {
+                if (want_plte) { // PLTE = -0.5 h^3 dd3 over (ring0, ring1, ring2, candidate)  (state_history.rs:40-56)
+                    const double hn = te - tr2;
+                    const double c3 = -1.0 / 12.0;
+                    const double alph = 6.0 * c3 * (hn * hn * hn);
+                    const double a01 = 1.0 / (tr1 - tr0), a12 = 1.0 / (tr2 - tr1), a23 = 1.0 / (te - tr2);
+                    const double a02 = 1.0 / (tr2 - tr0), a13 = 1.0 / (te - tr1), a03 = 1.0 / (te - tr0);
+                    const int o0 = (int)(nrec % 3), o1 = (int)((nrec + 1) % 3), o2 = (int)((nrec + 2) % 3);
+                    for (int i = l; i < n; i += G) {
+                        const double x0 = ring[o0 * n + i], x1 = ring[o1 * n + i], x2 = ring[o2 * n + i];
+                        const double x3 = x[i];
+                        const double d01 = a01 * (x1 - x0), d12 = a12 * (x2 - x1), d23 = a23 * (x3 - x2);
+                        const double d02 = a02 * (d12 - d01), d13 = a13 * (d23 - d12);
+                        const double d03 = a03 * (d13 - d02);
+                        const double pl = alph * d03;
+                        if (__ldg(&M.cls[i])) {
+                            pi += pl * pl;
+                            xi2 += x3 * x3;
+                        } else {
+                            pv += pl * pl;
+                            xv += x3 * x3;
+                        }
+                    }
+                }
+                Ops::sum2(pv, pi);
+                Ops::sum2(xv, xi2);
+            }
+            if (solved) {
+                if (r_newton == -ST_NOT_CONVERGED) {
+                    h *= 0.5;
+                    ci[CN_REJ_NEWTON]++;
+                } else if (nrec < 3) {
+                    accepted = true;
+                    nit = r_newton;
+                } else {
+                    const double plv = sqrt(pv) / (double)M.nv, pli = sqrt(pi) / (double)M.ni;
+                    const double xnv = sqrt(xv) / (double)M.nv, xni = sqrt(xi2) / (double)M.ni;
+                    const bool too_big = plv > xnv * 0.001 + 1e-3 || pli > xni * 0.001 + 1e-6; // transient.rs:99-101
+                    if (too_big) {
+                        h *= 0.5;
+                        ci[CN_REJ_PLTE]++;
+                    } else {
+                        accepted = true;
+                        nit = r_newton;
+                        const bool can_grow = plv < 0.1 * 1e-3 && pli < 0.1 * 1e-6; // :103-105
+                        next_h = (can_grow && h <= a.step_max / 2.0) ? h * 2.0 : h;
+                    }
+                }
+                if (!accepted && h < 1e-18) status = ST_TRAN_H_UNDERFLOW; // transient.rs:88-90
+                new_step = accepted;
+            }
+            if (__any_sync(0xffffffffu, accepted)) {
+                if (accepted) { // push the record (state_history.rs:24-30), write it out per the recording policy
+                    const int slot = (int)(nrec % 3);
+                    for (int i = l; i < n; i += G) ring[slot * n + i] = x[i];
+                    tr0 = tr1;
+                    tr1 = tr2;
+                    tr2 = te;
+                    const int stride = a.rec_stride > 1 ? a.rec_stride : 1;
+                    if (stored < a.cap && (nrec % stride) == 0) {
+                        const long long row = inst * a.cap + stored;
+                        if (a.x)
+                            for (int i = l; i < n; i += G) a.x[row * n + i] = x[i];
+                        if (l == 0) {
+                            if (a.t_out) a.t_out[row] = te;
+                            if (a.n_iters) a.n_iters[row] = nit;
+                        }
+                        ++stored;
+                    }
+                    ++nrec;
+                    ci[CN_POINTS]++;
+                    for (int i = l; i < DP.n_src; i += G) prev[3 * i + 1] = prev[3 * i + 2]; // vdd.rs:40-44, idd.rs:40-44
+                    t += h;
+                    // update_state with the accepted h (engine.rs:183-185; cap/model.rs:19-25, ind/model.rs:19-25)
+                    for (int i = l; i < DP.n_dyn; i += G) {
+                        const int *dd = &DP.dyn[6 * i];
+                        const int kind = __ldg(&dd[2]), vp = __ldg(&dd[3]), vn = __ldg(&dd[4]);
+                        const double u_old = state[2 * i], i_old = state[2 * i + 1], pvv = dynv[i];
+                        const double u_new = xat(x, vp) - xat(x, vn);
+                        double i_new;
+                        if (kind == K_C) {
+                            const double g = 2.0 * pvv / h;
+                            i_new = g * (u_new - u_old) - i_old;
+                        } else {
+                            const double g = h / (2.0 * pvv);
+                            i_new = g * (u_new + u_old) + i_old;
+                        }
+                        state[2 * i] = u_new;
+                        state[2 * i + 1] = i_new;
+                    }
+                    h = nrec <= 3 ? h : next_h; // the first three records keep h (transient.rs:55-59)
+                }
+                __syncwarp();
+            }
+        }
+        // ---------------------------------------------------------------- finished (or abandoned) instances
+        const bool done = have && (redo || status != ST_OK || !(t < a.t_stop));
+        if (__any_sync(0xffffffffu, done)) {
+            if (done) {
+                if (redo) { // left the plan: the warp kernel runs the instance from scratch (dynamic pivoting)
+                    if (l == 0) {
+                        a.redo_list[atomicAdd(a.redo_count, 1ULL)] = inst;
+                        a.status[inst] = ST_REDO;
+                    }
+                } else {
+                    if (a.x_final)
+                        for (int i = l; i < n; i += G) a.x_final[inst * n + i] = x[i];
+                    if (l == 0) {
+                        a.n_rec[inst] = nrec;
+                        a.status[inst] = status;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CN_LOCAL; ++i) cn[i] += ci[i];
+                }
+                have = false;
+            }
+            __syncwarp();
+        }
+    }
+    if (l == 0) {
+#pragma unroll
+        for (int i = 0; i < CN_LOCAL; ++i)
+            if (cn[i]) atomicAdd(&a.counters[i], cn[i]);
+    }
+}
+
+typedef void (*TeamKernelFn)(const RunArgs, const TeamArgs);
+TeamKernelFn team_kernel(int g, int place); // kern_team.cu
+
+} // namespace ftsb

@@ -1,0 +1,166 @@
+// team_plan.cpp — symbolic elimination along a fixed pivot sequence (team_plan.h)
+#include "team_plan.h"
+
+#include <algorithm>
+#include <map>
+
+namespace ftsb {
+
+TeamPlan TeamPlanHost::view(const int *b) const
+{
+    TeamPlan p;
+    p.n = n;
+    p.nA = nA;
+    p.S = S;
+    p.nJ = nJ;
+    p.arow = b + o_arow;
+    p.acol = b + o_acol;
+    p.aptr = b + o_aptr;
+    p.acon = b + o_acon;
+    p.sptr = b + o_sptr;
+    p.scon = b + o_scon;
+    p.pivrow = b + o_pivrow;
+    p.pive = b + o_pive;
+    p.tptr = b + o_tptr;
+    p.tgt = b + o_tgt;
+    p.tgtr = b + o_tgtr;
+    p.uptr = b + o_uptr;
+    p.updm = b + o_updm;
+    p.updds = b + o_updds;
+    p.bptr = b + o_bptr;
+    p.bwde = b + o_bwde;
+    p.bwdr = b + o_bwdr;
+    return p;
+}
+
+bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivseq, TeamPlanHost &out)
+{
+    const std::vector<int> &ib = comp.ints();
+    const ModeOff &mo = comp.mode[an];
+    const int n = mo.n;
+    if (n < 1 || (int)pivseq.size() != n) return false;
+    out = TeamPlanHost();
+    out.n = n;
+
+    // ---- A: the linear (+ companion) part, the matrix of the residual A x - b (mna.rs:25-29) ----
+    // an entry touched by a companion stamp carries its complete list in A_dyn (linear then companion contributions),
+    // every other entry its list in A_lin
+    std::map<int, std::vector<int>> a_ent; // row << 16 | col -> contribution words (row-major order of the keys)
+    auto take = [&](const GatherOff &g, bool overwrite) {
+        for (int d = 0; d < g.n_dst; ++d) {
+            const int dst = ib[g.dst + d], r = dst & 0xffff, c = dst >> 16;
+            const int key = (r << 16) | c;
+            if (!overwrite && a_ent.count(key)) continue;
+            std::vector<int> v(ib.begin() + g.con + ib[g.ptr + d], ib.begin() + g.con + ib[g.ptr + d + 1]);
+            a_ent[key] = v;
+        }
+    };
+    take(mo.A_lin, true);
+    take(mo.A_dyn, true);
+    std::vector<int> arow(n + 1, 0), acol, aptr{0}, acon;
+    for (auto &kv : a_ent) {
+        const int r = kv.first >> 16, c = kv.first & 0xffff;
+        arow[r + 1]++;
+        acol.push_back(c);
+        acon.insert(acon.end(), kv.second.begin(), kv.second.end());
+        aptr.push_back((int)acon.size());
+    }
+    for (int r = 0; r < n; ++r) arow[r + 1] += arow[r];
+    out.nA = (int)acol.size();
+
+    // ---- J: static entries in J_full order, then the fill-in of this pivot sequence ----
+    const GatherOff &jf = mo.J_full;
+    const int nJ = jf.n_dst;
+    std::vector<std::map<int, int>> rows(n); // row -> {col -> entry}
+    for (int d = 0; d < nJ; ++d) {
+        const int dst = ib[jf.dst + d];
+        rows[dst & 0xffff][dst >> 16] = d;
+    }
+    std::vector<int> sptr(ib.begin() + jf.ptr, ib.begin() + jf.ptr + nJ + 1), scon(ib.begin() + jf.con, ib.begin() + jf.con + jf.n_con);
+    int S = nJ;
+    std::vector<int> pos(n), piv(n);
+    for (int i = 0; i < n; ++i) pos[i] = piv[i] = i;
+    std::vector<int> pivrow(n), pive(n), tptr{0}, tgt, tgtr, uptr{0}, updm, updds;
+    for (int k = 0; k < n; ++k) {
+        const int P = pivseq[k];
+        if (P < 0 || P >= n || pos[P] < k) return false;
+        auto itp = rows[P].find(k);
+        if (itp == rows[P].end()) return false;
+        const int pP = pos[P];
+        pivrow[k] = P;
+        pive[k] = itp->second;
+        std::vector<int> tr;
+        for (int r = 0; r < n; ++r)
+            if (r != P && pos[r] >= k && rows[r].count(k)) tr.push_back(r);
+        for (int r : tr) {
+            const int em = rows[r][k];
+            tgt.push_back(em | (pos[r] < pP ? (1 << 30) : 0));
+            tgtr.push_back(r);
+            for (auto &pc : rows[P]) {
+                if (pc.first <= k) continue;
+                int dst;
+                auto it = rows[r].find(pc.first);
+                if (it == rows[r].end()) {
+                    dst = S++;
+                    rows[r][pc.first] = dst;
+                } else
+                    dst = it->second;
+                updm.push_back(em);
+                updds.push_back(dst | (pc.second << 16));
+            }
+            uptr.push_back((int)updm.size());
+        }
+        tptr.push_back((int)tgt.size());
+        const int rk = piv[k];
+        piv[k] = P;
+        piv[pP] = rk;
+        pos[P] = k;
+        pos[rk] = pP;
+    }
+    if (S >= 0xfff0 || out.nA >= 0xfff0) return false; // 16-bit entry indices in the packed lists
+    std::vector<int> bptr{0}, bwde, bwdr;
+    for (int i = 0; i < n; ++i) {
+        for (int r = 0; r < n; ++r) {
+            if (pos[r] >= i) continue;
+            auto it = rows[r].find(i);
+            if (it != rows[r].end()) {
+                bwde.push_back(it->second);
+                bwdr.push_back(r);
+            }
+        }
+        bptr.push_back((int)bwde.size());
+    }
+    out.S = S;
+    out.nJ = nJ;
+    out.nT = (int)tgt.size();
+    out.nU = (int)updm.size();
+    out.nB = (int)bwde.size();
+    out.flops_factor = (long long)n + out.nT + 2LL * out.nU;
+    out.flops_solve = 2LL * out.nT + n + 2LL * out.nB;
+    auto push = [&](const std::vector<int> &v) {
+        const int off = (int)out.ibuf.size();
+        out.ibuf.insert(out.ibuf.end(), v.begin(), v.end());
+        while (out.ibuf.size() & 3) out.ibuf.push_back(0);
+        return off;
+    };
+    out.o_arow = push(arow);
+    out.o_acol = push(acol);
+    out.o_aptr = push(aptr);
+    out.o_acon = push(acon);
+    out.o_sptr = push(sptr);
+    out.o_scon = push(scon);
+    out.o_pivrow = push(pivrow);
+    out.o_pive = push(pive);
+    out.o_tptr = push(tptr);
+    out.o_tgt = push(tgt);
+    out.o_tgtr = push(tgtr);
+    out.o_uptr = push(uptr);
+    out.o_updm = push(updm);
+    out.o_updds = push(updds);
+    out.o_bptr = push(bptr);
+    out.o_bwde = push(bwde);
+    out.o_bwdr = push(bwdr);
+    return true;
+}
+
+} // namespace ftsb

@@ -398,25 +398,41 @@ def _run_mid(circ, vals, fns, opts, cap=300):
 
 @pytest.mark.parametrize("which", ["ladder24", "ladder64", "inverter40", "ladder30_op", "inverter130"])
 def test_mid_size_kernels_agree_bitwise(which):
-    """Circuits with n > 16: the structure-exploiting warp kernel (default), the dense warp-per-instance kernel
+    """Circuits with n > 16: the per-team kernel (.tran default; 4 / 8 / 16 / 32 lanes per instance, slot table and
+    factors in shared or global memory), the structure-exploiting warp kernel, the dense warp-per-instance kernel
     (1-3 rows per lane, n <= 96) and the generic team / CTA kernel execute the same solution-path arithmetic on the
     non-zeros: every output must compare equal, and so must the work counters."""
     circ = _mid_circuit(which)
-    B = 5
+    B = 13
     vals, fns = nl.monte_carlo(circ, B)
-    v_sp, c_sp, o_sp = _run_mid(circ, vals, fns, {})
+    tran = circ.command("tran") is not None
+    v_def, c_def, o_def = _run_mid(circ, vals, fns, {})
+    v_sp, c_sp, o_sp = _run_mid(circ, vals, fns, {"team": 0})
+    assert v_sp.startswith("spw_n"), v_sp
+    assert c_sp["redo"] == 0, c_sp
+    if tran and which != "inverter130":
+        assert v_def.startswith("team"), v_def
+        for a, b in zip(o_sp, o_def):
+            assert np.array_equal(a, b, equal_nan=True), v_def
+        for lanes in (4, 8, 16, 32):
+            for place in (0, 1, 3):
+                v_t, c_t, o_t = _run_mid(circ, vals, fns, {"team_lanes": lanes, "team_place": place})
+                if not v_t.startswith("team"):  # does not fit in shared memory with that many instances per warp
+                    continue
+                assert v_t.startswith(f"team{lanes}p{place}"), v_t
+                assert c_t["redo"] == 0
+                for a, b in zip(o_sp, o_t):
+                    assert np.array_equal(a, b, equal_nan=True), v_t
     for forced in (0, 2):  # windowed elimination off / forced on (the default decides from the predicted structure)
-        _, c_f, o_f = _run_mid(circ, vals, fns, {"windowed": forced, "slots_global": forced // 2})
+        _, c_f, o_f = _run_mid(circ, vals, fns, {"team": 0, "windowed": forced, "slots_global": forced // 2})
         assert c_f["redo"] == 0
         for a, b in zip(o_sp, o_f):
             assert np.array_equal(a, b, equal_nan=True)
     v_w, _, o_w = _run_mid(circ, vals, fns, {"sparse_warp": 0})
     v_g, _, o_g = _run_mid(circ, vals, fns, {"force_generic": 1})
-    assert v_sp.startswith("spw_n"), v_sp
-    assert c_sp["redo"] == 0, c_sp
     n_start = circ.n_start
     assert (v_w.startswith("warp") and "r_n" in v_w) == (n_start <= 96), v_w
-    assert not ("r_n" in v_g) and not v_g.startswith("spw"), v_g
+    assert not ("r_n" in v_g) and not v_g.startswith(("spw", "team")), v_g
     for a, b, c in zip(o_sp, o_w, o_g):
         assert np.array_equal(a, b, equal_nan=True)
         assert np.array_equal(a, c, equal_nan=True)
@@ -429,7 +445,7 @@ def test_sparse_kernel_fill_pool_overflow_goes_to_the_dense_kernels(which):
     circ = _mid_circuit(which)
     vals, fns = nl.monte_carlo(circ, 7, rel=0.3)
     v0, c0, o0 = _run_mid(circ, vals, fns, {"sparse_warp": 0})
-    v1, c1, o1 = _run_mid(circ, vals, fns, {"fill_cap": 2})
+    v1, c1, o1 = _run_mid(circ, vals, fns, {"fill_cap": 2, "team": 0})
     assert v1.startswith("spw_n") and "redo" in v1, v1
     for a, b in zip(o0, o1):
         assert np.array_equal(a, b, equal_nan=True)
@@ -448,9 +464,11 @@ def test_sparse_kernel_singular_matrix_goes_to_the_dense_kernels(oracle_mod):
     assert (o[0] == st).all()
 
 
+@pytest.mark.parametrize("team", [0, 1])
 @pytest.mark.parametrize("which,B", [("inverter40", 64), ("ladder64", 48), ("inverter258", 6)])
-def test_sparse_kernel_vs_oracle(which, B, oracle_mod):
-    """The structure-exploiting kernel against the CPU oracle (dense elimination): status, record counts, iteration
+def test_sparse_kernel_vs_oracle(which, B, team, oracle_mod):
+    """The structure-exploiting warp kernel (team = 0) and the per-team kernel (team = 1; n = 258 is too large for it
+    and stays with the warp kernel) against the CPU oracle (dense elimination): status, record counts, iteration
     counts, time stamps equal; unknowns within 1e-9 / 1e-12."""
     if which == "inverter258":
         circ = nl.load(nl.inverter_chain_netlist(256, stop="0.4n", step="50p"))
@@ -459,9 +477,10 @@ def test_sparse_kernel_vs_oracle(which, B, oracle_mod):
     vals, fns = nl.monte_carlo(circ, B)
     t = circ.command("tran")
     be = BatchEngine(circ)
+    be.set_option("team", team)
     be.set_params(vals, fns)
     r = be.run_tran(t.stop, t.step, capacity=400)
-    assert be.variant.startswith("spw_n"), be.variant
+    assert be.variant.startswith("team" if team and which != "inverter258" else "spw_n"), be.variant
     st, nrec, it, tt, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals, fns, t.stop, t.step, 400, threads=8)
     assert (r.status == st).all() and (r.n_rec == nrec).all()
     for i in range(B):
@@ -642,7 +661,14 @@ def test_sparse_kernel_dc_sweep_and_record_stride(oracle_mod):
     be = BatchEngine(circ)
     be.set_params(vals, fns)
     rs = be.run_tran(t.stop, t.step, capacity=20, rec_stride=3)
-    assert be.variant.startswith("spw_n")
+    assert be.variant.startswith(("spw_n", "team"))
+    bw = BatchEngine(circ)
+    bw.set_option("team", 0)
+    bw.set_params(vals, fns)
+    rw = bw.run_tran(t.stop, t.step, capacity=20, rec_stride=3)
+    assert bw.variant.startswith("spw_n")
+    for a_, b_ in ((rs.t, rw.t), (rs.x, rw.x), (rs.n_iters, rw.n_iters), (rs.n_rec, rw.n_rec), (rs.x_final, rw.x_final)):
+        assert np.array_equal(a_, b_, equal_nan=True)
     assert (rs.n_rec == rf.n_rec).all() and (rs.status == rf.status).all()
     for i in range(B):
         kept = min(20, (int(rf.n_rec[i]) + 2) // 3)
