@@ -24,6 +24,9 @@ EXPORTS = [
     "ftsb_n_run", "ftsb_n_start", "ftsb_n_fn", "ftsb_set_option", "ftsb_set_params", "ftsb_run_op", "ftsb_run_dc",
     "ftsb_run_tran", "ftsb_sync", "ftsb_stream", "ftsb_set_stream", "ftsb_get_counters", "ftsb_launch_count",
     "ftsb_last_variant", "ftsb_lu_solve", "ftsb_measure_fp64_tflops", "ftsb_solve_op", "ftsb_solve_dc",
+    "ftsb_multi_compile", "ftsb_multi_destroy", "ftsb_multi_device_count", "ftsb_multi_last_error", "ftsb_multi_last_variant",
+    "ftsb_multi_set_option", "ftsb_multi_solve_op", "ftsb_multi_solve_dc", "ftsb_multi_solve_tran", "ftsb_multi_get_counters",
+    "ftsb_multi_launch_count",
 ]
 
 
@@ -109,6 +112,28 @@ def lib() -> ct.CDLL:
     L.ftsb_lu_solve.restype = ct.c_int
     L.ftsb_measure_fp64_tflops.argtypes = [ct.c_int]
     L.ftsb_measure_fp64_tflops.restype = d
+    L.ftsb_multi_compile.argtypes = [ct.POINTER(FtsbElem), i32, i32, i32, ct.POINTER(i32), ct.POINTER(i32), i32, ct.POINTER(vp)]
+    L.ftsb_multi_compile.restype = ct.c_int
+    L.ftsb_multi_destroy.argtypes = [vp]
+    L.ftsb_multi_destroy.restype = None
+    L.ftsb_multi_device_count.argtypes = [vp]
+    L.ftsb_multi_device_count.restype = i32
+    L.ftsb_multi_last_error.argtypes = [vp]
+    L.ftsb_multi_last_error.restype = ct.c_char_p
+    L.ftsb_multi_last_variant.argtypes = [vp]
+    L.ftsb_multi_last_variant.restype = ct.c_char_p
+    L.ftsb_multi_set_option.argtypes = [vp, ct.c_char_p, i64]
+    L.ftsb_multi_set_option.restype = ct.c_int
+    L.ftsb_multi_solve_op.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.ftsb_multi_solve_op.restype = ct.c_int
+    L.ftsb_multi_solve_dc.argtypes = [vp, i64, vp, vp, i32, vp, vp, vp, i64, vp, vp, vp, vp]
+    L.ftsb_multi_solve_dc.restype = ct.c_int
+    L.ftsb_multi_solve_tran.argtypes = [vp, i64, vp, vp, d, d, ct.POINTER(FtsbTranOpts), vp, vp, vp, vp, vp, vp]
+    L.ftsb_multi_solve_tran.restype = ct.c_int
+    L.ftsb_multi_get_counters.argtypes = [vp, ct.POINTER(FtsbCounters)]
+    L.ftsb_multi_get_counters.restype = ct.c_int
+    L.ftsb_multi_launch_count.argtypes = [vp]
+    L.ftsb_multi_launch_count.restype = i64
     _lib = L
     return L
 
@@ -116,4 +141,10 @@ def lib() -> ct.CDLL:
 def check(rc: int, handle=None) -> None:
     if rc != 0:
         msg = lib().ftsb_last_error(handle)
+        raise FtsbError(rc, msg.decode() if msg else "")
+
+
+def check_multi(rc: int, handle=None) -> None:
+    if rc != 0:
+        msg = lib().ftsb_multi_last_error(handle)
         raise FtsbError(rc, msg.decode() if msg else "")

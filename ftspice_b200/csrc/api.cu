@@ -26,6 +26,15 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device), not per handle: two handles on ONE device
+// driven by two host threads (ftsb_multi with a device listed twice) would change it under each other's launches, so the
+// plan-and-launch sequence of a run is serialised per device.  Launches are asynchronous: the lock is held for microseconds.
+std::mutex &device_launch_mutex(int device)
+{
+    static std::mutex mu[64];
+    return mu[device >= 0 && device < 64 ? device : 0];
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -712,7 +721,7 @@ int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
 // ---- per-team .tran kernels (solver_team.cuh) ----------------------------------------------------------------
 struct TeamLaunch {
     TeamKernelFn fn = nullptr;
-    int g = 0, place = 0, grid = 1;
+    int g = 0, place = 0, grid = 1, wpb = 4;
     size_t smem = 0, scratch_bytes = 0;
     TeamArgs ta{};
 };
@@ -747,42 +756,53 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     const int place = c->team_place >= 0 ? (c->team_place & 3) : (linear ? 0 : 3);
     // lanes per instance: rows are dealt round-robin, so few lanes waste little; more teams per warp amortise the
     // list-walking code over more instances but need more shared memory per warp
-    int best_g = 0, best_occ = 0;
+    int best_g = 0, best_occ = 0, best_wpb = 0;
     size_t best_smem = 0;
     TeamLayout best_lay{};
     for (int g : {8, 16, 32}) {
         if (c->team_g > 0) g = c->team_g;
-        TeamKernelFn fn = team_kernel(g, place);
+        TeamKernelFn fn = (mo.n + g - 1) / g <= 32 ? team_kernel(g, place, ph.ellW) : nullptr; // rows per lane fit a 32-bit class mask
         if (fn) {
             const int T = 32 / g;
-            const TeamLayout lay = team_layout(mo.n, ph.nA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place);
-            const size_t smem = (size_t)2 * FTS_LOG1P_N * 8 + (size_t)TEAM_WARPS * lay.sm_doubles * T * 8;
-            int occ = 0;
-            if (smem <= c->smem_optin &&
-                cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32 * TEAM_WARPS, smem) == cudaSuccess && occ >= 1) {
-                // automatic: the smallest lane count that keeps two warps per scheduler resident; a circuit too large for
-                // that (n = 258: 50 KB per instance) stays with the warp kernel and its global scratch rows
-                if (c->team_g > 0 || occ * TEAM_WARPS >= 8) {
-                    best_g = g;
-                    best_occ = occ;
-                    best_smem = smem;
-                    best_lay = lay;
-                }
-            } else
-                cudaGetLastError();
+            const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place);
+            int w_best = 0, occ_best = 0;
+            size_t smem_best = 0;
+            for (int wpb = TEAM_WARPS_MAX; wpb >= 1; --wpb) { // warps per block: whatever packs most warps onto an SM
+                const size_t smem = (size_t)2 * FTS_LOG1P_N * 8 + (size_t)wpb * lay.sm_doubles * T * 8;
+                int occ = 0;
+                if (smem <= c->smem_optin &&
+                    cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)fn, 32 * wpb, smem) == cudaSuccess && occ >= 1) {
+                    if (occ * wpb > occ_best * w_best) {
+                        w_best = wpb;
+                        occ_best = occ;
+                        smem_best = smem;
+                    }
+                } else
+                    cudaGetLastError();
+            }
+            // automatic: the smallest lane count that keeps two warps per scheduler resident; a circuit too large for
+            // that (n = 258: 50 KB per instance) stays with the warp kernel and its global scratch rows
+            if (w_best && (c->team_g > 0 || occ_best * w_best >= 8)) {
+                best_g = g;
+                best_occ = occ_best;
+                best_wpb = w_best;
+                best_smem = smem_best;
+                best_lay = lay;
+            }
         }
         if (c->team_g > 0 || best_g) break;
     }
     if (!best_g) return 1;
     const int T = 32 / best_g;
-    tl.fn = team_kernel(best_g, place);
+    tl.fn = team_kernel(best_g, place, ph.ellW);
     tl.g = best_g;
     tl.place = place;
+    tl.wpb = best_wpb;
     tl.smem = best_smem;
-    const long long per_block = (long long)TEAM_WARPS * T;
+    const long long per_block = (long long)best_wpb * T;
     tl.grid = (int)std::max(1LL, std::min((batch + per_block - 1) / per_block, (long long)best_occ * c->sm_count));
-    tl.scratch_bytes = (size_t)tl.grid * TEAM_WARPS * best_lay.gl_doubles * T * 8;
+    tl.scratch_bytes = (size_t)tl.grid * best_wpb * best_lay.gl_doubles * T * 8;
     tl.ta.plan = ph.view((const int *)c->team_buf.p);
     tl.ta.lay = best_lay;
     tl.ta.flops_factor = ph.flops_factor;
@@ -792,7 +812,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
         return 1;
     }
     c->variant = "team" + std::to_string(best_g) + "p" + std::to_string(place) + "_n" + std::to_string(mo.n) + "/A" + std::to_string(ph.nA) +
-                 "/S" + std::to_string(ph.S) + "/occ" + std::to_string(best_occ * TEAM_WARPS);
+                 "/S" + std::to_string(ph.S) + (ph.chain ? "/chain" : "") + "/occ" + std::to_string(best_occ) + "x" + std::to_string(best_wpb);
     return 0;
 }
 
@@ -802,7 +822,7 @@ int launch_team(ftsb_circuit *c, TeamLaunch &tl, RunArgs &a)
     tl.ta.gscratch = (double *)c->team_scratch.p;
     FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
     void *args[] = {&a, &tl.ta};
-    FTSB_CUDA(c, cudaLaunchKernel((const void *)tl.fn, dim3(tl.grid), dim3(32 * TEAM_WARPS), args, tl.smem, c->stream));
+    FTSB_CUDA(c, cudaLaunchKernel((const void *)tl.fn, dim3(tl.grid), dim3(32 * tl.wpb), args, tl.smem, c->stream));
     c->launches++;
     return 0;
 }
@@ -892,6 +912,7 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
 
 int launch(ftsb_circuit *c, int an, RunArgs &a)
 {
+    std::lock_guard<std::mutex> device_lock(device_launch_mutex(c->device));
     a.prog = c->prog;
     a.work = (unsigned long long *)c->work.p;
     a.counters = (unsigned long long *)c->counters.p;
@@ -1358,6 +1379,7 @@ int solve_pipelined_impl(ftsb_circuit *c, int an, long long B, const PipeIo &io,
 {
     int rc = pipe_init(c);
     if (rc) return rc;
+    std::unique_lock<std::mutex> device_lock(device_launch_mutex(c->device));
     const int ne = c->comp.n_elems, nf = c->comp.n_fn;
     const int n = an == AN_OP ? c->comp.n_start : c->comp.n_run;
     const long long P = io.P;
@@ -1455,6 +1477,7 @@ int solve_pipelined_impl(ftsb_circuit *c, int an, long long B, const PipeIo &io,
     if (rc) return rc;
     unsigned long long n_redo = 0;
     FTSB_CUDA(c, cudaMemcpyAsync(&n_redo, a.redo_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    device_lock.unlock(); // everything is enqueued: other handles of this device may plan and launch while this one waits
     FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (n_redo) {
         rc = d2h(c->stream, 0, B);
@@ -1857,7 +1880,9 @@ extern "C" int ftsb_debug_jit(const ftsb_elem *elems, int32_t n_elems, int32_t n
 
 // ---------------------------------------------------------------------------------------------------------
 // diagnostics (not part of include/ftsb.h): the static elimination plan of the per-team kernels, built without a GPU.
-// meta[0..6] = n, nA, S, nJ, nT, nU, nB; meta[7..23] = the 17 list offsets in TeamPlanHost order; meta[24] = ints used.
+// meta[0..6] = n, nA, S, nJ, nT, nU, nB; meta[7..23] = the 17 list offsets in TeamPlanHost order; meta[24] = ints used;
+// meta[25..40] = ellW, nSlotA, chain, nFop, nBop, nFchunk, nBchunk and the offsets of fop, fvidx, fchunk, bop, bvidx, bchunk,
+// ellcol, ovfptr, ovfcol.
 // jdst[nJ] = row | col << 16 of the static entries, piv[n] = the pivot sequence the plan follows.
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t n_start, const int32_t *row_class,
@@ -1878,6 +1903,9 @@ extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int
                      ph.o_pivrow, ph.o_pive, ph.o_tptr, ph.o_tgt, ph.o_tgtr, ph.o_uptr, ph.o_updm, ph.o_updds, ph.o_bptr, ph.o_bwde,
                      ph.o_bwdr, (int)ph.ibuf.size()};
     std::copy(m, m + 25, meta);
+    const int m2[] = {ph.ellW, ph.nSlotA, ph.chain, ph.nFop, ph.nBop, ph.nFchunk, ph.nBchunk, ph.o_fop, ph.o_fvidx, ph.o_fchunk,
+                      ph.o_bop, ph.o_bvidx, ph.o_bchunk, ph.o_ellcol, ph.o_ovfptr, ph.o_ovfcol};
+    std::copy(m2, m2 + 16, meta + 25); // meta[25..40]
     for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
     std::copy(pv.begin(), pv.end(), piv);
     return 0;

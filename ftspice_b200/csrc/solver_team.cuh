@@ -32,7 +32,7 @@ namespace ftsb {
 
 // offsets in doubles per team; an array lives in shared memory or in the warp's global region ("g" offsets)
 struct TeamLayout {
-    int ox, oxp, ob, oy, oA, oprev;      // shared
+    int ox, oxp, ob, oy, oA, oprev, ostg; // shared (stg: two chunks of substitution operands, team_plan.h)
     int oval, osv, oalpha;               // shared (PLACE bits 0 / 1) or global
     int ostate, oring, odynv;            // global
     int sm_doubles, gl_doubles;
@@ -54,12 +54,13 @@ __host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_sl
         go += c;
         return r;
     };
-    t.ox = ts(n);
-    t.oxp = ts(n);
-    t.ob = ts(n);
+    t.ox = ts(n + 1); // + the zero row (team_plan.h)
+    t.oxp = ts(n + 1);
+    t.ob = ts(n + 1);
     t.oy = ts(n);
     t.oA = ts(nA);
     t.oprev = ts(3 * n_src);
+    t.ostg = ts(2 * TEAM_CHUNK);
     t.oval = (place & 1) ? ts(n_slots) : tg(n_slots);
     t.osv = (place & 2) ? ts(S) : tg(S);
     t.oalpha = (place & 2) ? ts(n) : tg(n);
@@ -78,7 +79,7 @@ struct TeamArgs {
     long long flops_factor, flops_solve;
 };
 
-constexpr int TEAM_WARPS = 4; // warps per block (they share the ln_1p table)
+constexpr int TEAM_WARPS_MAX = 8; // warps per block (they share the ln_1p table); the launcher picks the count
 
 template <int G>
 struct TeamOps {
@@ -117,7 +118,7 @@ struct TeamOps {
     static __device__ __forceinline__ void assemble(const TeamPlan &P, V val, V A, V sv, int l, bool on)
     {
         if (on) {
-            for (int e = l; e < P.nA; e += G) {
+            for (int e = l; e < P.nSlotA; e += G) { // (ELL padding slots have no contribution: 0.0)
                 double acc = 0.0;
                 const int c0 = __ldg(&P.aptr[e]), c1 = __ldg(&P.aptr[e + 1]);
                 for (int c = c0; c < c1; ++c) {
@@ -244,6 +245,142 @@ struct TeamOps {
         return ok;
     }
 
+    // y / d for a d whose correctly rounded reciprocal al = 1.0 / d is at hand: q0 = y * al is within an ulp of the
+    // quotient, the exact remainder r = y - d * q0 (one FMA) corrects it, and q0 + r * al rounds to the correctly
+    // rounded quotient (Markstein) as long as nothing overflows / underflows — checked on the exponents; everything
+    // else (zero, tiny, huge, infinite, NaN operands) takes the division itself.  Bit-identical to y / d
+    // (tests: test_team_exact_division_*), five instructions instead of ~30 on the critical path of the back substitution.
+    static __device__ __forceinline__ double div_known_rcp(double y, double d, double al)
+    {
+        const unsigned ey = ((unsigned)__double2hiint(y) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(d) >> 20) & 0x7ffu;
+        if (ey - 623u < 800u && ed - 623u < 800u) { // both magnitudes in [2^-400, 2^400)
+            const double q0 = y * al;
+            const double r0 = fma(-d, q0, y);
+            return fma(r0, al, q0);
+        }
+        return y / d;
+    }
+    // s / c for a small positive integer c (class sizes): same construction; s >= 0 is a square root, zero or normal
+    static __device__ __forceinline__ double div_count(double s, double c, double rc)
+    {
+        if (s < __longlong_as_double(0x7ff0000000000000LL)) {
+            const double q0 = s * rc;
+            const double r0 = fma(-c, q0, s);
+            return fma(r0, rc, q0);
+        }
+        return s / c; // inf, NaN
+    }
+
+    // The substitutions as op streams (team_plan.h): lane 0 of the team walks the ops in order — a chain of dependent
+    // updates on a ladder — with the value it just wrote kept in a register; all lanes of the team fetch the factor
+    // entries the ops need one chunk ahead (one L2 latency per TEAM_CHUNK ops instead of one per op) and hand them over
+    // through a double-buffered staging area in shared memory.
+    // forward: y through the stored multipliers (gauss_lu.rs:40)
+    static __device__ void chain_forward(const TeamPlan &P, V sva, V y, V stg, int l, bool on)
+    {
+        constexpr int VPL = TEAM_CHUNK / G;
+        double vreg[VPL];
+        const int nchunk = P.nFchunk;
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+            const int idx = __ldg(&P.fvidx[u * G + l]);
+            vreg[u] = on ? sva[idx] : 0.0;
+        }
+        double last_v = 0.0;
+        int last_r = -1;
+        int o0 = __ldg(&P.fchunk[0]);
+        for (int c = 0; c < nchunk; ++c) {
+            const V buf = stg + (c & 1) * TEAM_CHUNK;
+#pragma unroll
+            for (int u = 0; u < VPL; ++u) buf[u * G + l] = vreg[u];
+            __syncwarp();
+            if (c + 1 < nchunk) {
+#pragma unroll
+                for (int u = 0; u < VPL; ++u) {
+                    const int idx = __ldg(&P.fvidx[(c + 1) * TEAM_CHUNK + u * G + l]);
+                    vreg[u] = on ? sva[idx] : 0.0;
+                }
+            }
+            const int o1 = __ldg(&P.fchunk[c + 1]);
+            if (on && l == 0) {
+                int slot = 0;
+                for (int op = o0; op < o1; ++op, ++slot) {
+                    const int w0 = __ldg(&P.fop[op]);
+                    const int r = w0 & 0xffff, pk = (w0 >> 16) & 0xffff;
+                    const double m = buf[slot];
+                    if (m != 0.0) {
+                        const double ypk = pk == last_r ? last_v : y[pk];
+                        const double yr = r == last_r ? last_v : y[r];
+                        const double v = yr - m * ypk;
+                        y[r] = v;
+                        last_r = r;
+                        last_v = v;
+                    }
+                }
+            }
+            o0 = o1;
+        }
+        __syncwarp();
+    }
+    // backward: gauss_lu.rs:44-53; false when a solution component is not finite
+    static __device__ bool chain_backward(const TeamPlan &P, V sva, V y, V xp, V stg, int l, bool on, unsigned tmask)
+    {
+        constexpr int VPL = TEAM_CHUNK / G;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        double vreg[VPL];
+        const int nchunk = P.nBchunk;
+#pragma unroll
+        for (int u = 0; u < VPL; ++u) {
+            const int idx = __ldg(&P.bvidx[u * G + l]);
+            vreg[u] = on ? sva[idx] : 0.0;
+        }
+        double last_v = 0.0, xi = 0.0;
+        int last_r = -1;
+        bool bad = false;
+        int o0 = __ldg(&P.bchunk[0]);
+        for (int c = 0; c < nchunk; ++c) {
+            const V buf = stg + (c & 1) * TEAM_CHUNK;
+#pragma unroll
+            for (int u = 0; u < VPL; ++u) buf[u * G + l] = vreg[u];
+            __syncwarp();
+            if (c + 1 < nchunk) {
+#pragma unroll
+                for (int u = 0; u < VPL; ++u) {
+                    const int idx = __ldg(&P.bvidx[(c + 1) * TEAM_CHUNK + u * G + l]);
+                    vreg[u] = on ? sva[idx] : 0.0;
+                }
+            }
+            const int o1 = __ldg(&P.bchunk[c + 1]);
+            if (on && l == 0) {
+                int slot = 0;
+                for (int op = o0; op < o1; ++op) {
+                    const int2 w = __ldg(reinterpret_cast<const int2 *>(P.bop) + op);
+                    if (w.y < 0) { // x_i = y[pivot row] / pivot
+                        const int pi = w.x & 0xffff, i = (w.x >> 16) & 0xffff;
+                        const double d = buf[slot], al = buf[slot + 1];
+                        slot += 2;
+                        const double yv = pi == last_r ? last_v : y[pi];
+                        xi = div_known_rcp(yv, d, al);
+                        xp[i] = xi;
+                        bad |= !(fabs(xi) < INF);
+                    } else { // y[r] -= x_i * u(r, i)
+                        const int r = w.x;
+                        const double uv = buf[slot];
+                        slot += 1;
+                        const double yr = r == last_r ? last_v : y[r];
+                        const double v = yr - xi * uv;
+                        y[r] = v;
+                        last_r = r;
+                        last_v = v;
+                    }
+                }
+            }
+            o0 = o1;
+        }
+        __syncwarp();
+        return !any(bad, tmask);
+    }
+
     // nonlinear devices at x -> slot values; returns team-wide (#non-finite currents) | panic << 20
     static __device__ __forceinline__ int eval_nl(const ModeProg &M, V x, V val, int l, bool on)
     {
@@ -262,8 +399,8 @@ struct TeamOps {
 };
 
 // place: see team_layout
-template <int G, int PLACE>
-__global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_constant__ RunArgs a, const __grid_constant__ TeamArgs ta)
+template <int G, int PLACE, int W>
+__global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __grid_constant__ RunArgs a, const __grid_constant__ TeamArgs ta)
 {
     using Ops = TeamOps<G>;
     constexpr int T = Ops::T;
@@ -284,13 +421,31 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
     const int q = lane / G, l = lane % G;
     const unsigned tmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
     double *sw = tab + 2 * FTS_LOG1P_N + (size_t)warp * L.sm_doubles * T + q;
-    double *gw = ta.gscratch + ((size_t)blockIdx.x * TEAM_WARPS + warp) * (size_t)L.gl_doubles * T + q;
+    double *gw = ta.gscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)L.gl_doubles * T + q;
     const V x{sw + L.ox * T}, xp{sw + L.oxp * T}, b{sw + L.ob * T}, y{sw + L.oy * T}, A{sw + L.oA * T}, prev{sw + L.oprev * T};
+    const V stg{sw + L.ostg * T};
     const V val{((PLACE & 1) ? sw : gw) + L.oval * T};
     const V sv{((PLACE & 2) ? sw : gw) + L.osv * T}, alpha{((PLACE & 2) ? sw : gw) + L.oalpha * T};
     const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T};
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const bool linear = M.n_nl == 0;
+    const bool chain = P.chain != 0;
+    const int R = (n + G - 1) / G; // rows per lane: row i = j * G + l, j < R
+    unsigned clsmask = 0;          // bit j: row j * G + l is a current row (NodeType::Current); R <= 32 (launcher)
+    for (int j = 0; j < R && j < 32; ++j) {
+        const int i = j * G + l;
+        if (i < n && __ldg(&M.cls[i])) clsmask |= 1u << j;
+    }
+    auto is_cur = [&](int j, int) -> bool { return ((clsmask >> j) & 1u) != 0u; };
+    const double dnv = (double)M.nv, dni = (double)M.ni, rnv = 1.0 / dnv, rni = 1.0 / dni;
+    const bool has_ovf = P.nSlotA > W * (n + 1);
+    // the zero row (index n of x, x_proposed, b; row n of A): written once, never touched by an instance
+    if (l == 0) {
+        x[n] = 0.0;
+        xp[n] = 0.0;
+        b[n] = 0.0;
+    }
+    __syncwarp();
 
     // per-team state (uniform over the lanes of a team)
     bool have = false, exhausted = false, new_step = true;
@@ -432,8 +587,13 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
             __syncwarp();
             bool it_on = act && !redo; // still iterating
             if (linear) { // one pair of substitutions per attempt: J == A, the proposed solution does not move
-                Ops::forward(P, sv, y, l, it_on);
-                if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                if (chain) {
+                    Ops::chain_forward(P, sv, y, stg, l, it_on);
+                    if (!Ops::chain_backward(P, sv, y, xp, stg, l, it_on, tmask) && it_on) redo = true;
+                } else {
+                    Ops::forward(P, sv, y, l, it_on);
+                    if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                }
                 if (it_on) {
                     ci[CN_SOLVE]++;
                     ci[CN_FLOPS] += (unsigned long long)ta.flops_solve;
@@ -462,8 +622,13 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
                     Ops::assemble_sv(P, val, sv, l, it_on);
                     __syncwarp();
                     if (Ops::factor(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
-                    Ops::forward(P, sv, y, l, it_on);
-                    if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                    if (chain) {
+                        Ops::chain_forward(P, sv, y, stg, l, it_on);
+                        if (!Ops::chain_backward(P, sv, y, xp, stg, l, it_on, tmask) && it_on) redo = true;
+                    } else {
+                        Ops::forward(P, sv, y, l, it_on);
+                        if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                    }
                     if (it_on) {
                         ci[CN_FACTOR]++;
                         ci[CN_SOLVE]++;
@@ -474,52 +639,88 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
                 }
                 double qv = 0.0, qi = 0.0;
                 if (it_on) { // damped step (newtons_method.rs:73-77); x is updated in place (x = x_new, :57-59)
-                    for (int i = l; i < n; i += G) {
-                        const double xi = x[i];
-                        const double d = xp[i] - xi;
-                        const double tt = (1.3 / 16.0) * copysign(1.0, d) * fts_log1p_pos(16.0 * fabs(d), tab);
-                        x[i] = xi + tt;
-                        if (__ldg(&M.cls[i]))
-                            qi += tt * tt;
-                        else
-                            qv += tt * tt;
+                    constexpr int RB = 3; // rows in flight per lane: their ln_1p chains interleave
+                    for (int j0 = 0; j0 < R; j0 += RB) {
+                        double xi_[RB], d_[RB], tt_[RB];
+                        int i_[RB];
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            i_[u] = min((j0 + u) * G + l, n); // past the last row: the zero row (d = 0, t = 0)
+                            xi_[u] = x[i_[u]];
+                            d_[u] = xp[i_[u]] - xi_[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < RB; ++u)
+                            tt_[u] = (1.3 / 16.0) * copysign(1.0, d_[u]) * fts_log1p_pos(16.0 * fabs(d_[u]), tab);
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            x[i_[u]] = xi_[u] + tt_[u];
+                            if (is_cur(j0 + u, 0))
+                                qi += tt_[u] * tt_[u];
+                            else
+                                qv += tt_[u] * tt_[u];
+                        }
                     }
                 }
                 Ops::sum2(qv, qi);
-                svn = sqrt(qv) / (double)M.nv;
-                sin_ = sqrt(qi) / (double)M.ni;
+                svn = Ops::div_count(sqrt(qv), dnv, rnv);
+                sin_ = Ops::div_count(sqrt(qi), dni, rni);
                 __syncwarp();
                 flags = Ops::eval_nl(M, x, val, l, it_on);
                 double fv = 0.0, fi = 0.0;
                 if (it_on) { // f = A x + H g - b (mna.rs:25-29) and its class norms (node_vec_norm.rs:12-33)
                     const int nbad = flags & 0xfffff;
-                    for (int row = l; row < n; row += G) {
-                        double ax = 0.0;
-                        const int c0 = __ldg(&P.arow[row]), c1 = __ldg(&P.arow[row + 1]);
-                        for (int c = c0; c < c1; ++c) ax = ax + A[c] * x[__ldg(&P.acol[c])];
-                        double hg = 0.0;
-                        if (!linear) {
-                            int own_bad = 0;
-                            const int f0 = __ldg(&M.f_nl.ptr[row]), f1 = __ldg(&M.f_nl.ptr[row + 1]);
-                            for (int c = f0; c < f1; ++c) {
-                                const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
-                                const double v = val[wd & ~CON_NEG];
-                                own_bad += isfinite(v) ? 0 : 1;
-                                hg += (wd & CON_NEG) ? -v : v;
-                            }
-                            if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
+                    constexpr int RB = 3;
+                    for (int j0 = 0; j0 < R; j0 += RB) {
+                        int2 cols[RB];
+                        int row_[RB];
+                        double ax[RB];
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            row_[u] = min((j0 + u) * G + l, n); // past the last row: the zero row (f = 0)
+                            cols[u] = __ldg(reinterpret_cast<const int2 *>(P.ellcol) + row_[u]);
+                            ax[u] = 0.0;
                         }
-                        const double f = ax + hg - b[row];
-                        if (__ldg(&M.cls[row]))
-                            fi += f * f;
-                        else
-                            fv += f * f;
+#pragma unroll
+                        for (int w = 0; w < W; ++w) { // the row's entries in column order, a(r, c) * x(c) with separate multiply and add
+#pragma unroll
+                            for (int u = 0; u < RB; ++u) {
+                                const int cw = w < 2 ? cols[u].x : cols[u].y;
+                                const int col = (w & 1) ? (cw >> 16) & 0xffff : cw & 0xffff;
+                                ax[u] = ax[u] + A[row_[u] * W + w] * x[col];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < RB; ++u) {
+                            const int row = row_[u];
+                            if (has_ovf && row < n) {
+                                const int v0 = __ldg(&P.ovfptr[row]), v1 = __ldg(&P.ovfptr[row + 1]);
+                                for (int c = v0; c < v1; ++c) ax[u] = ax[u] + A[W * (n + 1) + c] * x[__ldg(&P.ovfcol[c])]; // long rows
+                            }
+                            double hg = 0.0;
+                            if (!linear && row < n) {
+                                int own_bad = 0;
+                                const int f0 = __ldg(&M.f_nl.ptr[row]), f1 = __ldg(&M.f_nl.ptr[row + 1]);
+                                for (int c = f0; c < f1; ++c) {
+                                    const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
+                                    const double v = val[wd & ~CON_NEG];
+                                    own_bad += isfinite(v) ? 0 : 1;
+                                    hg += (wd & CON_NEG) ? -v : v;
+                                }
+                                if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
+                            }
+                            const double f = ax[u] + hg - b[row];
+                            if (is_cur(j0 + u, 0))
+                                fi += f * f;
+                            else
+                                fv += f * f;
+                        }
                     }
                 }
                 Ops::sum2(fv, fi);
                 if (it_on) {
-                    ev = sqrt(fv) / (double)M.nv;
-                    ei = sqrt(fi) / (double)M.ni;
+                    ev = Ops::div_count(sqrt(fv), dnv, rnv);
+                    ei = Ops::div_count(sqrt(fi), dni, rni);
                     if ((flags >> 20) || isinf(ev) || isinf(ei)) { // the reference panics: reproduced from scratch by the warp kernel
                         redo = true;
                         it_on = false;
@@ -548,14 +749,17 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
                     const double a01 = 1.0 / (tr1 - tr0), a12 = 1.0 / (tr2 - tr1), a23 = 1.0 / (te - tr2);
                     const double a02 = 1.0 / (tr2 - tr0), a13 = 1.0 / (te - tr1), a03 = 1.0 / (te - tr0);
                     const int o0 = (int)(nrec % 3), o1 = (int)((nrec + 1) % 3), o2 = (int)((nrec + 2) % 3);
-                    for (int i = l; i < n; i += G) {
+#pragma unroll 3
+                    for (int j = 0; j < R; ++j) {
+                        const int i = j * G + l;
+                        if (i >= n) break;
                         const double x0 = ring[o0 * n + i], x1 = ring[o1 * n + i], x2 = ring[o2 * n + i];
                         const double x3 = x[i];
                         const double d01 = a01 * (x1 - x0), d12 = a12 * (x2 - x1), d23 = a23 * (x3 - x2);
                         const double d02 = a02 * (d12 - d01), d13 = a13 * (d23 - d12);
                         const double d03 = a03 * (d13 - d02);
                         const double pl = alph * d03;
-                        if (__ldg(&M.cls[i])) {
+                        if (is_cur(j, i)) {
                             pi += pl * pl;
                             xi2 += x3 * x3;
                         } else {
@@ -575,8 +779,8 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
                     accepted = true;
                     nit = r_newton;
                 } else {
-                    const double plv = sqrt(pv) / (double)M.nv, pli = sqrt(pi) / (double)M.ni;
-                    const double xnv = sqrt(xv) / (double)M.nv, xni = sqrt(xi2) / (double)M.ni;
+                    const double plv = Ops::div_count(sqrt(pv), dnv, rnv), pli = Ops::div_count(sqrt(pi), dni, rni);
+                    const double xnv = Ops::div_count(sqrt(xv), dnv, rnv), xni = Ops::div_count(sqrt(xi2), dni, rni);
                     const bool too_big = plv > xnv * 0.001 + 1e-3 || pli > xni * 0.001 + 1e-6; // transient.rs:99-101
                     if (too_big) {
                         h *= 0.5;
@@ -667,6 +871,6 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS) k_team_tran(const __grid_cons
 }
 
 typedef void (*TeamKernelFn)(const RunArgs, const TeamArgs);
-TeamKernelFn team_kernel(int g, int place); // kern_team.cu
+TeamKernelFn team_kernel(int g, int place, int ell_w); // kern_team.cu
 
 } // namespace ftsb

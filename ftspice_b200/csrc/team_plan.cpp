@@ -30,6 +30,22 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.bptr = b + o_bptr;
     p.bwde = b + o_bwde;
     p.bwdr = b + o_bwdr;
+    p.ellW = ellW;
+    p.nSlotA = nSlotA;
+    p.ellcol = b + o_ellcol;
+    p.ovfptr = b + o_ovfptr;
+    p.ovfcol = b + o_ovfcol;
+    p.chain = chain;
+    p.nFop = nFop;
+    p.nBop = nBop;
+    p.nFchunk = nFchunk;
+    p.nBchunk = nBchunk;
+    p.fop = b + o_fop;
+    p.fvidx = b + o_fvidx;
+    p.fchunk = b + o_fchunk;
+    p.bop = b + o_bop;
+    p.bvidx = b + o_bvidx;
+    p.bchunk = b + o_bchunk;
     return p;
 }
 
@@ -57,16 +73,46 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
     };
     take(mo.A_lin, true);
     take(mo.A_dyn, true);
-    std::vector<int> arow(n + 1, 0), acol, aptr{0}, acon;
+    std::vector<int> arow(n + 1, 0), acol;
+    std::vector<std::vector<std::pair<int, const std::vector<int> *>>> by_row(n); // row -> (col, contributions), columns ascending
     for (auto &kv : a_ent) {
         const int r = kv.first >> 16, c = kv.first & 0xffff;
         arow[r + 1]++;
         acol.push_back(c);
-        acon.insert(acon.end(), kv.second.begin(), kv.second.end());
-        aptr.push_back((int)acon.size());
+        by_row[r].push_back({c, &kv.second});
     }
     for (int r = 0; r < n; ++r) arow[r + 1] += arow[r];
     out.nA = (int)acol.size();
+    int maxlen = 0;
+    for (int r = 0; r < n; ++r) maxlen = std::max(maxlen, (int)by_row[r].size());
+    const int W = std::max(3, std::min(4, maxlen)); // the kernels are built for 3 and 4 ELL slots per row
+    // rows 0 .. n-1 and one ZERO row n (all slots 0.0, columns n): lanes dealt a row index >= n in the last round of a
+    // row loop clamp it to n instead of branching
+    std::vector<int> ellcol(2 * (n + 1), 0), ovfptr{0}, ovfcol;
+    std::vector<std::vector<int>> slot_con((size_t)W * (n + 1)); // contributions of A slot row * W + w (empty: 0.0)
+    for (int r = 0; r <= n; ++r) {
+        int cols[4] = {r, r, r, r};
+        if (r < n)
+            for (int w = 0; w < (int)by_row[r].size(); ++w) {
+                if (w < W) {
+                    cols[w] = by_row[r][w].first;
+                    slot_con[(size_t)r * W + w] = *by_row[r][w].second;
+                } else {
+                    ovfcol.push_back(by_row[r][w].first);
+                    slot_con.push_back(*by_row[r][w].second);
+                }
+            }
+        ellcol[2 * r] = cols[0] | (cols[1] << 16);
+        ellcol[2 * r + 1] = cols[2] | (cols[3] << 16);
+        if (r < n) ovfptr.push_back((int)ovfcol.size());
+    }
+    std::vector<int> aptr{0}, acon;
+    for (auto &v : slot_con) {
+        acon.insert(acon.end(), v.begin(), v.end());
+        aptr.push_back((int)acon.size());
+    }
+    out.ellW = W;
+    out.nSlotA = (int)slot_con.size();
 
     // ---- J: static entries in J_full order, then the fill-in of this pivot sequence ----
     const GatherOff &jf = mo.J_full;
@@ -117,7 +163,7 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
         pos[P] = k;
         pos[rk] = pP;
     }
-    if (S >= 0xfff0 || out.nA >= 0xfff0) return false; // 16-bit entry indices in the packed lists
+    if (S + n >= 0xfff0 || out.nSlotA >= 0xfff0 || n >= 0x7ff0) return false; // 16-bit indices in the packed lists
     std::vector<int> bptr{0}, bwde, bwdr;
     for (int i = 0; i < n; ++i) {
         for (int r = 0; r < n; ++r) {
@@ -129,6 +175,70 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
             }
         }
         bptr.push_back((int)bwde.size());
+    }
+    // ---- substitutions as op streams with chunked value slots ----
+    {
+        int maxt = 0;
+        for (int k = 0; k < n; ++k) maxt = std::max(maxt, tptr[k + 1] - tptr[k]);
+        int maxb = 0;
+        for (int i = 0; i < n; ++i) maxb = std::max(maxb, bptr[i + 1] - bptr[i]);
+        out.chain = (maxt <= 2 && maxb <= 2) ? 1 : 0; // ladders, chains of two-terminal stages; a supply rail has wide steps
+        std::vector<int> fop, fvidx, fchunk{0}, bop, bvidx, bchunk{0};
+        // an op's value slots lie inside one chunk; a chunk that is full (or too full for the op) is closed first
+        auto begin_op = [&](std::vector<int> &vidx, std::vector<int> &chunk, int n_ops_so_far, int nvals) {
+            int used = (int)(vidx.size() % TEAM_CHUNK);
+            if (used + nvals > TEAM_CHUNK) {
+                while (vidx.size() % TEAM_CHUNK) vidx.push_back(0);
+                used = 0;
+            }
+            if (used == 0 && !vidx.empty()) chunk.push_back(n_ops_so_far);
+        };
+        auto end_stream = [&](std::vector<int> &vidx, std::vector<int> &chunk, int n_ops) {
+            if (vidx.empty()) vidx.push_back(0);
+            while (vidx.size() % TEAM_CHUNK) vidx.push_back(0);
+            chunk.push_back(n_ops);
+        };
+        for (int k = 0; k < n; ++k)
+            for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) {
+                begin_op(fvidx, fchunk, (int)fop.size(), 1);
+                fop.push_back(tgtr[tt] | (pivrow[k] << 16));
+                fvidx.push_back(tgt[tt] & 0xffff);
+            }
+        end_stream(fvidx, fchunk, (int)fop.size());
+        for (int i = n - 1; i >= 0; --i) {
+            begin_op(bvidx, bchunk, (int)bop.size() / 2, 2);
+            bop.push_back(pivrow[i] | (i << 16));
+            bop.push_back(-1);
+            bvidx.push_back(pive[i]);
+            bvidx.push_back(S + i);
+            for (int bb = bptr[i]; bb < bptr[i + 1]; ++bb) {
+                begin_op(bvidx, bchunk, (int)bop.size() / 2, 1);
+                bop.push_back(bwdr[bb]);
+                bop.push_back(0);
+                bvidx.push_back(bwde[bb]);
+            }
+        }
+        end_stream(bvidx, bchunk, (int)bop.size() / 2);
+        out.nFop = (int)fop.size();
+        out.nBop = (int)bop.size() / 2;
+        out.nFchunk = (int)fchunk.size() - 1;
+        out.nBchunk = (int)bchunk.size() - 1;
+        if (out.nFchunk * TEAM_CHUNK != (int)fvidx.size() || out.nBchunk * TEAM_CHUNK != (int)bvidx.size()) return false;
+        auto push2 = [&](const std::vector<int> &v) {
+            const int off = (int)out.ibuf.size();
+            out.ibuf.insert(out.ibuf.end(), v.begin(), v.end());
+            while (out.ibuf.size() & 3) out.ibuf.push_back(0);
+            return off;
+        };
+        out.o_fop = push2(fop);
+        out.o_fvidx = push2(fvidx);
+        out.o_fchunk = push2(fchunk);
+        out.o_bop = push2(bop);
+        out.o_bvidx = push2(bvidx);
+        out.o_bchunk = push2(bchunk);
+        out.o_ellcol = push2(ellcol);
+        out.o_ovfptr = push2(ovfptr);
+        out.o_ovfcol = push2(ovfcol);
     }
     out.S = S;
     out.nJ = nJ;

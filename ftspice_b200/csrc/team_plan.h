@@ -36,13 +36,39 @@ struct TeamPlan {
     const int *bptr;        // [n + 1] entries of U in column i (rows at final positions < i)
     const int *bwde;        // [nB] entry
     const int *bwdr;        // [nB] row
+    // ---- residual in ELL form: row r holds its first ellW (3 or 4) entries at A slots r * ellW + w (padding: value 0.0,
+    //      column r); row n is a ZERO row (lanes dealt a row >= n clamp to it); the entries of longer rows follow at slots
+    //      ellW * (n + 1) + k (ovf lists).  aptr / acon are indexed by slot.
+    int ellW, nSlotA;       // slots of A: ellW * (n + 1) + overflow entries
+    const int *ellcol;      // [n + 1][2] columns of the row's ELL entries, 16 bits each
+    const int *ovfptr;      // [n + 1]
+    const int *ovfcol;      // [n_ovf]
+    // ---- substitutions as single-lane op streams (one lane of a team walks them; the values they need are staged
+    //      through shared memory in chunks of TEAM_CHUNK by all lanes of the team).  Value indices address the factors
+    //      array followed by the reciprocal pivots (index S + k).
+    //      forward op : x = m entry value slot;  word0 = row r | pivot row << 16
+    //      backward op: word1 < 0: divide — word0 = pivot row | column i << 16, two value slots (pivot, its reciprocal);
+    //                   else update — word0 = row r, one value slot (entry of U); uses the x_i of the last divide
+    int chain, nFop, nBop, nFchunk, nBchunk; // chain = 1: every elimination step has few targets, use the streams
+    const int *fop;         // [nFop] word0
+    const int *fvidx;       // [nFchunk * TEAM_CHUNK] value index of slot (padding: 0)
+    const int *fchunk;      // [nFchunk + 1] ops of chunk c: [fchunk[c], fchunk[c + 1]); their value slots are consecutive from
+                            //              the start of the chunk
+    const int *bop;         // [nBop][2]
+    const int *bvidx;       // [nBchunk * TEAM_CHUNK]
+    const int *bchunk;      // [nBchunk + 1]
 };
+
+constexpr int TEAM_CHUNK = 32;
 
 struct TeamPlanHost {
     int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0;
     std::vector<int> ibuf;
     int o_arow = 0, o_acol = 0, o_aptr = 0, o_acon = 0, o_sptr = 0, o_scon = 0, o_pivrow = 0, o_pive = 0, o_tptr = 0, o_tgt = 0,
         o_tgtr = 0, o_uptr = 0, o_updm = 0, o_updds = 0, o_bptr = 0, o_bwde = 0, o_bwdr = 0;
+    int ellW = 0, nSlotA = 0, o_ellcol = 0, o_ovfptr = 0, o_ovfcol = 0;
+    int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,
+        o_bchunk = 0;
     long long flops_factor = 0, flops_solve = 0; // floating-point operations of one factorisation / one pair of substitutions
     TeamPlan view(const int *base) const;
 };

@@ -308,6 +308,122 @@ class BatchEngine:
                                             v(nrec_ptr), v(xf_ptr), v(st_ptr), capi.MEM_DEVICE), self.h)
 
 
+class MultiEngine:
+    """One compiled topology on a LIST of GPUs (ftsb_multi_*): the batch is sharded contiguously inside the library, one
+    host thread per device, results written straight into the caller's arrays — the device count does not show in the
+    output layout.  Host buffers only."""
+
+    def __init__(self, circ: nl.Circuit, devices: Optional[Sequence[int]] = None):
+        self.circ = circ
+        L = capi.lib()
+        ne = circ.n_elems
+        elems = (capi.FtsbElem * max(ne, 1))()
+        for i in range(ne):
+            elems[i].kind = int(circ.kind[i])
+            for j in range(3):
+                elems[i].node[j] = int(circ.node[i, j])
+            elems[i].branch = int(circ.branch[i])
+            elems[i].fn_kind = int(circ.fn_kind[i])
+        cls = np.ascontiguousarray(circ.cls, np.int32)
+        devs = np.ascontiguousarray(devices if devices is not None else [], np.int32)
+        h = ct.c_void_p()
+        rc = L.ftsb_multi_compile(elems, ne, circ.n_run, circ.n_start, cls.ctypes.data_as(ct.POINTER(ct.c_int32)),
+                                  devs.ctypes.data_as(ct.POINTER(ct.c_int32)) if len(devs) else None, len(devs), ct.byref(h))
+        capi.check_multi(rc, None)
+        self.h = h
+        self.fn_elems = [i for i in range(ne) if circ.kind[i] in (nl.V, nl.I) and circ.fn_kind[i] != nl.FN_NONE]
+        self.n_fn = len(self.fn_elems)
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            capi.lib().ftsb_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_devices(self) -> int:
+        return int(capi.lib().ftsb_multi_device_count(self.h))
+
+    @property
+    def variant(self) -> str:
+        return capi.lib().ftsb_multi_last_variant(self.h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(capi.lib().ftsb_multi_launch_count(self.h))
+
+    def set_option(self, name: str, value: int) -> None:
+        capi.check_multi(capi.lib().ftsb_multi_set_option(self.h, name.encode(), int(value)), self.h)
+
+    def counters(self) -> dict:
+        c = capi.FtsbCounters()
+        capi.check_multi(capi.lib().ftsb_multi_get_counters(self.h, ct.byref(c)), self.h)
+        return {k: int(getattr(c, k)) for k in ("solve_points", "newton_iters", "lu_factor", "lu_solve", "rej_newton",
+                                                "rej_plte", "redo", "sparse_flops")}
+
+    def _host_params(self, vals: np.ndarray, fns: Optional[np.ndarray]):
+        c = self.circ
+        vals = np.ascontiguousarray(vals, np.float64)
+        B = vals.shape[0]
+        if fns is None:
+            fns = np.broadcast_to(c.fns, (B, c.n_elems, 7))
+        fns = np.asarray(fns)
+        if fns.shape[1] == c.n_elems:
+            fns = fns[:, self.fn_elems, :]
+        return vals, np.ascontiguousarray(fns, np.float64), B
+
+    def solve_op(self, vals: np.ndarray, fns: Optional[np.ndarray] = None) -> OpResult:
+        vals, fns, B = self._host_params(vals, fns)
+        x = np.zeros((B, self.circ.n_start))
+        it = np.zeros(B, np.int32)
+        st = np.zeros(B, np.int32)
+        capi.check_multi(capi.lib().ftsb_multi_solve_op(self.h, B, _ptr(vals), _ptr(fns) if self.n_fn else None, _ptr(x), _ptr(it),
+                                                        _ptr(st)), self.h)
+        return OpResult(st, it, x)
+
+    def solve_dc(self, vals: np.ndarray, fns: Optional[np.ndarray], source: Union[str, int], start, stop, step,
+                 max_points: Optional[int] = None) -> DcResult:
+        vals, fns, B = self._host_params(vals, fns)
+        n = self.circ.n_run
+        se = self.circ.elem_index(source) if isinstance(source, str) else int(source)
+        start = np.ascontiguousarray(np.broadcast_to(np.asarray(start, np.float64), (B,)))
+        stop = np.ascontiguousarray(np.broadcast_to(np.asarray(stop, np.float64), (B,)))
+        step = np.ascontiguousarray(np.broadcast_to(np.asarray(step, np.float64), (B,)))
+        counts = np.ceil((stop - start) / step)
+        counts = np.where(counts >= 0, counts, 0).astype(np.int64)
+        P = int(max_points or max(int(counts.max()), 1))
+        x = np.zeros((B, P, n))
+        it = np.zeros((B, P), np.int32)
+        done = np.zeros(B, np.int64)
+        st = np.zeros(B, np.int32)
+        capi.check_multi(capi.lib().ftsb_multi_solve_dc(self.h, B, _ptr(vals), _ptr(fns) if self.n_fn else None, se, _ptr(start),
+                                                        _ptr(stop), _ptr(step), P, _ptr(x), _ptr(it), _ptr(done), _ptr(st)), self.h)
+        sweep = start[:, None] + step[:, None] * np.arange(P, dtype=np.float64)[None, :]
+        return DcResult(st, done, it, x, sweep)
+
+    def solve_tran(self, vals: np.ndarray, fns: Optional[np.ndarray], stop: float, step: float, capacity: int = 0,
+                   rec_stride: int = 1) -> TranResult:
+        vals, fns, B = self._host_params(vals, fns)
+        n = self.circ.n_run
+        cap = int(capacity)
+        t = np.zeros((B, cap)) if cap else None
+        x = np.zeros((B, cap, n)) if cap else None
+        it = np.zeros((B, cap), np.int32) if cap else None
+        nrec = np.zeros(B, np.int64)
+        xf = np.zeros((B, n))
+        st = np.zeros(B, np.int32)
+        opts = capi.FtsbTranOpts(cap, rec_stride, 0)
+        capi.check_multi(capi.lib().ftsb_multi_solve_tran(self.h, B, _ptr(vals), _ptr(fns) if self.n_fn else None, float(stop),
+                                                          float(step), ct.byref(opts), _ptr(t), _ptr(x), _ptr(it), _ptr(nrec),
+                                                          _ptr(xf), _ptr(st)), self.h)
+        return TranResult(st, nrec, it, t, x, xf)
+
+
 def _raise_for(status: int) -> None:
     if status in (capi.NOT_CONVERGED, capi.TRAN_H_UNDERFLOW):
         raise NotConvergedError(status)

@@ -18,8 +18,9 @@
  *                        (src/engine/newtons_method.rs:53-55, src/device/nmos/model.rs:38-40)
  *
  * Everything is plain C: pointers and sizes, no C++ or torch types.  Every call returns 0 on success
- * or a negative FTSB_E_* code; ftsb_last_error() gives the text.  One handle = one CUDA device and one
- * stream; a handle is used by one thread at a time.  There is NO CPU fallback: without a usable CUDA
+ * or a negative FTSB_E_* code; ftsb_last_error() gives the text.  An ftsb_circuit handle = one CUDA device
+ * and one stream (an ftsb_multi handle = a list of devices, sharding internal); a handle is used by one
+ * thread at a time.  There is NO CPU fallback: without a usable CUDA
  * device ftsb_compile fails with FTSB_E_CUDA.
  *
  * A *batch* is a set of independent circuit instances sharing one topology: Monte-Carlo parameter
@@ -173,6 +174,34 @@ int ftsb_solve_dc(ftsb_circuit *c, int64_t batch, const double *vals, const doub
  * NULL), status[batch]. */
 int ftsb_run_tran(ftsb_circuit *c, double stop, double step_max, const ftsb_tran_opts *opts, double *t, double *x,
                   int32_t *n_iters, int64_t *n_rec, double *x_final, int32_t *status, int mem);
+
+/* ---- several devices behind one handle ----
+ * The instances of a batch are independent: the batch is cut into contiguous shards, one per device of
+ * the list (devices == NULL or n_devices <= 0: every visible device; a device may be listed more than once), each
+ * device has its own compiled copy of the topology and its own host thread (pinned to the cores of the GPU's NUMA node;
+ * FTSB_NUMA_PIN=0 in the environment switches that off), and every shard's results are written straight into the caller's HOST
+ * buffers at the shard's offset: the output layout is that of a single-device call, the device count is invisible.
+ * No collective, no process group: this is what the Rust side of src/main.rs:29-44 calls on a multi-GPU box.
+ * Instance-major parameters only.  ftsb_multi_solve_* = Engine::new values + Engine::run_op / run_dc / run_tran
+ * (src/engine.rs:31-60, :62-90, :92-140, :142-206) for every instance, blocking. */
+typedef struct ftsb_multi ftsb_multi; /* opaque */
+int ftsb_multi_compile(const ftsb_elem *elems, int32_t n_elems, int32_t n_run, int32_t n_start, const int32_t *row_class,
+                       const int32_t *devices, int32_t n_devices, ftsb_multi **out);
+void ftsb_multi_destroy(ftsb_multi *m);
+int32_t ftsb_multi_device_count(const ftsb_multi *m);
+const char *ftsb_multi_last_error(const ftsb_multi *m);
+const char *ftsb_multi_last_variant(const ftsb_multi *m);
+int ftsb_multi_set_option(ftsb_multi *m, const char *name, int64_t value); /* forwarded to every device's handle */
+int ftsb_multi_solve_op(ftsb_multi *m, int64_t batch, const double *vals, const double *fn, double *x, int32_t *n_iters,
+                        int32_t *status);
+int ftsb_multi_solve_dc(ftsb_multi *m, int64_t batch, const double *vals, const double *fn, int32_t sweep_elem,
+                        const double *start, const double *stop, const double *step, int64_t max_points, double *x,
+                        int32_t *n_iters, int64_t *points_done, int32_t *status);
+int ftsb_multi_solve_tran(ftsb_multi *m, int64_t batch, const double *vals, const double *fn, double stop, double step_max,
+                          const ftsb_tran_opts *opts, double *t, double *x, int32_t *n_iters, int64_t *n_rec, double *x_final,
+                          int32_t *status);
+int ftsb_multi_get_counters(ftsb_multi *m, ftsb_counters *out); /* summed over the devices */
+int64_t ftsb_multi_launch_count(const ftsb_multi *m);
 
 /* ---- plumbing ---- */
 int ftsb_sync(ftsb_circuit *c);                          /* wait for the handle's stream */

@@ -68,7 +68,8 @@ def _run_and_check(which, opts, oracle_mod, live):
         assert int(r.n_iters[j, :k].sum()) == i["newton_iters"]
         for row, xr in zip(i["rows"], i["x_rows"]):
             assert_close(r.x[j, row], np.array([float(v) for v in xr]), f"{which} instance {i['index']} record {row}")
-        assert_close(r.x_final[j], np.array([float(v) for v in i["x_final"]]), f"{which} instance {i['index']} final")
+        if i["status"] == 0:  # (a failing instance ends inside a Newton limit cycle: its last iterate is not an output row)
+            assert_close(r.x_final[j], np.array([float(v) for v in i["x_final"]]), f"{which} instance {i['index']} final")
     # live oracle on a few instances (failing ones included): every record
     st, nrec, it, t, x, xf, _ = oracle_mod.Oracle(circ).batch_tran(vals[live], fns[live], fx["stop"], fx["step"], cap,
                                                                    threads=len(live))

@@ -94,7 +94,7 @@ def test_tran_current_source_small_circuits_all_families(name, oracle_mod):
         else:  # same solution-path arithmetic in every family: the same bits
             for a, b in zip(ref, out):
                 assert np.array_equal(a, b, equal_nan=True), (name, opts, v)
-    assert len(seen) >= 4, seen
+    assert len(seen) >= 3, seen  # lanes kernel, generic sub-warp kernel, CTA kernel
 
 
 @pytest.mark.gpu

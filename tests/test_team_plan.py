@@ -36,7 +36,7 @@ def team_plan(circ, an=2):
     cls = np.ascontiguousarray(circ.cls, np.int32)
     cap = 1 << 22
     ibuf = np.zeros(cap, np.int32)
-    meta = np.zeros(32, np.int32)
+    meta = np.zeros(64, np.int32)
     jdst = np.zeros(1 << 18, np.int32)
     piv = np.zeros(1 << 12, np.int32)
     rc = fn(elems, circ.n_elems, circ.n_run, circ.n_start, cls.ctypes.data, an, ibuf.ctypes.data, cap, meta.ctypes.data,
@@ -52,12 +52,58 @@ def team_plan(circ, an=2):
     for k, o in zip(offs, meta[7:24]):
         if k in lens:
             p[k] = ibuf[int(o):int(o) + lens[k]].copy()
+    for k, v in zip(["ellW", "nSlotA", "chain", "nFop", "nBop", "nFchunk", "nBchunk"], meta[25:32]):
+        p[k] = int(v)
+    lens2 = {"fop": p["nFop"], "fvidx": p["nFchunk"] * 32, "fchunk": p["nFchunk"] + 1, "bop": 2 * p["nBop"],
+             "bvidx": p["nBchunk"] * 32, "bchunk": p["nBchunk"] + 1, "ellcol": 2 * (p["n"] + 1), "ovfptr": p["n"] + 1}
+    for k, o in zip(["fop", "fvidx", "fchunk", "bop", "bvidx", "bchunk", "ellcol", "ovfptr", "ovfcol"], meta[32:41]):
+        if k in lens2:
+            p[k] = ibuf[int(o):int(o) + lens2[k]].copy()
+        else:
+            p[k] = ibuf[int(o):int(o) + int(p["ovfptr"][-1])].copy()
     p["jdst"] = jdst[:p["nJ"]].copy()
     p["piv"] = piv[:p["n"]].copy()
     return p
 
 
-def run_plan(p, vals, rhs):
+def run_streams(p, sv, alpha, rhs):
+    """The kernel's chain_forward / chain_backward: op streams, values staged in chunks of 32 slots."""
+    n, S = p["n"], p["S"]
+    sva = np.concatenate([sv, alpha])
+    y = rhs.copy()
+    for c in range(p["nFchunk"]):
+        buf = sva[p["fvidx"][32 * c:32 * c + 32]]
+        slot = 0
+        for op in range(p["fchunk"][c], p["fchunk"][c + 1]):
+            w0 = int(p["fop"][op])
+            r, pk = w0 & 0xffff, (w0 >> 16) & 0xffff
+            m = buf[slot]
+            slot += 1
+            if m != 0.0:
+                y[r] = y[r] - m * y[pk]
+    x = np.full(n, np.nan)
+    xi = 0.0
+    for c in range(p["nBchunk"]):
+        buf = sva[p["bvidx"][32 * c:32 * c + 32]]
+        slot = 0
+        for op in range(p["bchunk"][c], p["bchunk"][c + 1]):
+            w0, w1 = int(p["bop"][2 * op]), int(p["bop"][2 * op + 1])
+            if w1 < 0:
+                pi, i = w0 & 0xffff, (w0 >> 16) & 0xffff
+                d, al = buf[slot], buf[slot + 1]
+                slot += 2
+                assert al == alpha[i]
+                xi = y[pi] / d
+                x[i] = xi
+            else:
+                y[w0] = y[w0] - xi * buf[slot]
+                slot += 1
+        assert slot <= 32
+    assert p["fchunk"][-1] == p["nFop"] and p["bchunk"][-1] == p["nBop"]
+    return x
+
+
+def run_plan(p, vals, rhs, streams=False):
     """The kernel's factor / forward / backward (solver_team.cuh) in numpy float64 scalars."""
     n, S = p["n"], p["S"]
     sv = np.zeros(S)
@@ -75,6 +121,8 @@ def run_plan(p, vals, rhs):
             if m != 0.0:
                 d, s = p["updds"][u] & 0xffff, (p["updds"][u] >> 16) & 0xffff
                 sv[d] = sv[d] - m * sv[s]
+    if streams:
+        return run_streams(p, sv, alpha, rhs)
     y = rhs.copy()
     for k in range(n):
         for tt in range(p["tptr"][k], p["tptr"][k + 1]):
@@ -139,6 +187,7 @@ def test_plan_equals_dense_elimination_bitwise(which):
         x_dense = dense_same_pivots(n, a, rhs, p["piv"].tolist())
         assert np.all(np.isfinite(x_dense))
         assert np.array_equal(x_plan, x_dense), (which, trial, np.abs(x_plan - x_dense).max())
+        assert np.array_equal(run_plan(p, vals, rhs, streams=True), x_dense), (which, trial, "op streams")
         assert np.abs(a @ x_plan - rhs).max() < 1e-6 * max(1.0, np.abs(x_plan).max())
 
 
@@ -153,6 +202,53 @@ def test_plan_a_entries_are_the_linear_part():
             a_keys.add((r, int(p["acol"][c])))
     j_keys = {(int(d) & 0xffff, int(d) >> 16) for d in p["jdst"]}
     assert a_keys == j_keys
+    # the residual's ELL form: a tridiagonal ladder needs three slots per row and no overflow; the columns of a row are
+    # its CSR columns in order, padding slots point at the row itself; row n is the zero row
+    assert p["ellW"] == 3 and p["nSlotA"] == 3 * (p["n"] + 1) and p["ovfptr"][-1] == 0 and p["chain"] == 1
+    n = p["n"]
+    assert [int(p["ellcol"][2 * n]) & 0xffff, int(p["ellcol"][2 * n]) >> 16, int(p["ellcol"][2 * n + 1]) & 0xffff] == [n, n, n]
+    for r in range(p["n"]):
+        cols = [int(p["ellcol"][2 * r]) & 0xffff, (int(p["ellcol"][2 * r]) >> 16) & 0xffff, int(p["ellcol"][2 * r + 1]) & 0xffff]
+        want = [int(c) for c in p["acol"][p["arow"][r]:p["arow"][r + 1]]]
+        assert cols[:len(want)] == want and all(c == r for c in cols[len(want):])
     circ = nl.load(CIRCUITS["inverter40"]())
     p = team_plan(circ)
     assert p["nA"] < p["nJ"]  # the NMOS gate columns exist in J only
+    assert p["chain"] == 0 and p["ovfptr"][-1] > 0 and p["ellW"] == 4  # the supply rail: wide elimination steps, a long row
+
+
+@pytest.mark.gpu
+def test_team_exact_division_equals_plain_division_bitwise():
+    """The back substitution divides by a pivot whose correctly rounded reciprocal is known (solver_team.cuh,
+    div_known_rcp): the result must be the IEEE quotient bit for bit — random operands over the guarded exponent range
+    and beyond it (zeros, denormals, huge, infinities, NaN take the plain division)."""
+    lib = capi.lib()
+    fn = lib.ftsb_debug_div
+    fn.argtypes = [ct.c_int, ct.c_longlong, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p]
+    fn.restype = ct.c_int
+    rng = np.random.default_rng(11)
+    n = 1 << 23
+
+    def rnd(emin, emax, special):
+        man = rng.integers(0, 1 << 52, n, dtype=np.uint64)
+        if special:
+            k = rng.integers(0, 4, n)
+            man = np.where(k == 0, np.uint64((1 << 52) - 1) - rng.integers(0, 16, n, dtype=np.uint64), man)
+            man = np.where(k == 1, rng.integers(0, 16, n, dtype=np.uint64), man)
+            man = np.where(k == 2, rng.integers(0, 256, n, dtype=np.uint64) << np.uint64(44), man)
+        e = rng.integers(emin + 1023, emax + 1024, n, dtype=np.uint64)
+        s = rng.integers(0, 2, n, dtype=np.uint64)
+        return ((s << np.uint64(63)) | (e << np.uint64(52)) | man).view(np.float64)
+
+    for (e0, e1, special) in ((-60, 60, True), (-399, 399, False), (-1022, 1023, False)):
+        y, d = rnd(e0, e1, special), rnd(e0, e1, special)
+        if e0 < -1000:  # sprinkle the operands the guard must route to the plain division
+            y[:64] = np.resize([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1.7e308], 64)
+            d[64:128] = np.resize([5e-324, 1e-310, 1.7e308, np.inf], 64)
+        fast, ref = np.zeros(n), np.zeros(n)
+        assert fn(0, n, y.ctypes.data, d.ctypes.data, fast.ctypes.data, ref.ctypes.data) == 0
+        same = (fast.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(fast) & np.isnan(ref))
+        assert same.all(), (e0, e1, int((~same).sum()), y[~same][:3], d[~same][:3])
+        with np.errstate(all="ignore"):
+            host = y / d
+        assert ((ref.view(np.uint64) == host.view(np.uint64)) | (np.isnan(ref) & np.isnan(host))).all()
