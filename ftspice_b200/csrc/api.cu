@@ -69,6 +69,7 @@ struct ftsb_circuit {
     DevBuf ibuf;
     DevProg prog{};
     long long batch = 0;
+    long long vs_inst = 0, vs_elem = 1, fs_inst = 0, fs_elem = 1; // layout of the device copies of the parameters (RunArgs)
     DevBuf vals, fn, tmp_in, work, counters, scratch;
     // staging of outputs when the caller's buffers are on the host
     DevBuf o_x, o_it, o_status, o_done, o_t, o_nrec, o_xf, i_start, i_stop, i_step;
@@ -127,7 +128,10 @@ struct ftsb_circuit {
     int team_state = 0;    // 0 = not tried, 1 = plan on the device, -1 = no usable plan
     int team_opt = 1;      // option "team": 1 (default) use them, 0 = the warp-per-instance kernels as before
     int team_g = 0;        // option "team_lanes": lanes per instance (0 = automatic)
-    int team_place = -1;   // option "team_place": bit 0 slot table, bit 1 factors in shared memory (-1 = automatic)
+    int team_place = -1;   // option "team_place": 0 slot table and factors in global scratch, 3 in shared memory (-1 = automatic)
+    int l2_persist = 1;    // option "l2_persist": keep the per-warp global scratch rows resident in L2 (access policy window)
+    size_t l2_set_aside = 0, l2_window_max = 0;
+    bool l2_queried = false;
     int sparse = 0;        // 1: zero-skipping thread-per-instance kernels for n <= 16; 0 (default): dense elimination,
                            // G lanes per instance -- measured faster on B200 (the thread-per-instance mapping fits only
                            // 2-3 warps per SM in shared memory and is latency bound)
@@ -684,7 +688,8 @@ int launch_jit_range(ftsb_circuit *c, int an, RunArgs &a, cudaStream_t stream, u
     const double *vals = a.vals, *fn = a.fn, *st = a.start, *sp = a.stop, *se = a.step;
     long long batch = end, max_points = a.max_points;
     void *params[] = {&vals, &fn, &batch, &work, &a.counters, &a.x, &a.n_iters, &a.status, &a.redo_list, &a.redo_count,
-                      &st, &sp, &se, &max_points, &a.points_done, &sweep_slot, &stop_it, &resume};
+                      &st, &sp, &se, &max_points, &a.points_done, &sweep_slot, &stop_it, &resume, &a.vs_inst, &a.vs_elem,
+                      &a.fs_inst, &a.fs_elem};
     // every resident slot: lanes refill as their instances finish, so 65 536 instances on 37 888 lanes take 1.73 instance times
     // (a grid of 1 024 warps = two whole rounds per lane measured 0.82 ms against 0.705 ms)
     const int grid = (int)std::max(1LL, std::min((end - begin + 31) / 32, (long long)c->jit_occ[an] * c->sm_count));
@@ -716,6 +721,40 @@ int launch_jit(ftsb_circuit *c, int an, RunArgs &a)
         if (rc) return rc;
     }
     return 0;
+}
+
+// The global scratch rows of the warp / team kernels (slot tables, vectors, per-step history of the resident instances) are
+// re-read and re-written every Newton iteration / accepted step.  They fit in L2 (tens of MB), but ordinary lines are
+// evicted by the streaming parameter and waveform traffic and written back to HBM over and over (round 1, C5: 7.3 GB of
+// DRAM writes per 0.28 s launch for 3 MB of results).  An access-policy window marks the scratch as persisting in a
+// set-aside part of L2; everything else streams past it.  Best effort: failures are ignored.
+void l2_persist_window(ftsb_circuit *c, void *base, size_t bytes)
+{
+    if (!c->l2_queried) {
+        c->l2_queried = true;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t want = (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                c->l2_set_aside = want;
+                c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+            }
+        }
+        cudaGetLastError();
+    }
+    if (!c->l2_set_aside || !c->l2_window_max) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (c->l2_persist && base && bytes) {
+        const size_t win = std::min(bytes, c->l2_window_max);
+        attr.accessPolicyWindow.base_ptr = base;
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_set_aside / (double)win);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } // else: num_bytes = 0 switches the window off
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
 }
 
 // ---- per-team .tran kernels (solver_team.cuh) ----------------------------------------------------------------
@@ -820,6 +859,7 @@ int launch_team(ftsb_circuit *c, TeamLaunch &tl, RunArgs &a)
 {
     FTSB_CUDA(c, c->team_scratch.ensure(tl.scratch_bytes));
     tl.ta.gscratch = (double *)c->team_scratch.p;
+    l2_persist_window(c, c->team_scratch.p, tl.scratch_bytes);
     FTSB_CUDA(c, cudaMemsetAsync(c->work.p, 0, 8, c->stream));
     void *args[] = {&a, &tl.ta};
     FTSB_CUDA(c, cudaLaunchKernel((const void *)tl.fn, dim3(tl.grid), dim3(32 * tl.wpb), args, tl.smem, c->stream));
@@ -890,8 +930,10 @@ int run_phase(ftsb_circuit *c, int an, RunArgs a, std::string &variant)
         FTSB_CUDA(c, cudaMemsetAsync(as.redo_count, 0, 8, c->stream));
         if (c->last_redo_an >= 0 && c->last_redo_an != an && c->last_redo_an < 2)
             c->redo_traced[c->last_redo_an] = false; // its redo count is gone: do not relearn from a stale counter
+        if (!planned && ps.scratch_bytes) l2_persist_window(c, c->scratch.p, ps.scratch_bytes);
         rc = use_jit ? launch_jit(c, an, as) : launch_kernel(c, ps, as);
         if (rc) return rc;
+        if (!planned && ps.scratch_bytes) l2_persist_window(c, nullptr, 0);
         a.in_list = as.redo_list;
         a.in_count = as.redo_count;
         if (planned && c->relearn_left[an] > 0) { // the dense redo pass records what the plans did not cover
@@ -914,6 +956,10 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
 {
     std::lock_guard<std::mutex> device_lock(device_launch_mutex(c->device));
     a.prog = c->prog;
+    a.vs_inst = c->vs_inst;
+    a.vs_elem = c->vs_elem;
+    a.fs_inst = c->fs_inst;
+    a.fs_elem = c->fs_elem;
     a.work = (unsigned long long *)c->work.p;
     a.counters = (unsigned long long *)c->counters.p;
     a.skip_refactor = c->skip_refactor;
@@ -958,22 +1004,6 @@ int launch(ftsb_circuit *c, int an, RunArgs &a)
     if (rc) return rc;
     c->variant = ext_start ? v_main + "+op[" + v_op + "]" : v_main;
     return 0;
-}
-
-__global__ void k_transpose(const double *__restrict__ in, double *__restrict__ out, long long rows, long long cols)
-{
-    // in[rows][cols] -> out[cols][rows]
-    __shared__ double tile[32][33];
-    long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        long long r = r0 + j, cc = c0 + threadIdx.x;
-        if (r < rows && cc < cols) tile[j][threadIdx.x] = in[r * cols + cc];
-    }
-    __syncthreads();
-    for (int j = threadIdx.y; j < 32; j += 8) {
-        long long cc = c0 + j, r = r0 + threadIdx.x;
-        if (r < rows && cc < cols) out[cc * rows + r] = tile[threadIdx.x][j];
-    }
 }
 
 // the generated kernels depend on an option that changed: wait for work in flight (an asynchronous FTSB_MEM_DEVICE run may
@@ -1138,6 +1168,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
     }
     else if (!strcmp(name, "sparse_warp"))
         c->sparse_warp = value ? 1 : 0;
+    else if (!strcmp(name, "l2_persist"))
+        c->l2_persist = value ? 1 : 0;
     else if (!strcmp(name, "team"))
         c->team_opt = value ? 1 : 0;
     else if (!strcmp(name, "team_lanes"))
@@ -1188,24 +1220,10 @@ int ftsb_set_params(ftsb_circuit *c, int64_t batch, const double *vals, const do
     FTSB_CUDA(c, c->vals.ensure(vb));
     FTSB_CUDA(c, c->fn.ensure(fb));
     const cudaMemcpyKind kind = mem == FTSB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    // either layout is kept as it comes: the kernels address element e of instance i as p[i * s_inst + e * s_elem]
     auto put = [&](DevBuf &dst, const double *src, long long inner) -> int {
         if (inner == 0 || !src) return 0;
-        const size_t bytes = (size_t)batch * inner * 8;
-        if (layout == FTSB_LAYOUT_INSTANCE_MAJOR) {
-            FTSB_CUDA(c, cudaMemcpyAsync(dst.p, src, bytes, kind, c->stream));
-        } else { // [inner][batch] -> [batch][inner]
-            const double *dsrc = src;
-            if (mem == FTSB_MEM_HOST) {
-                FTSB_CUDA(c, c->tmp_in.ensure(bytes));
-                FTSB_CUDA(c, cudaMemcpyAsync(c->tmp_in.p, src, bytes, kind, c->stream));
-                dsrc = (const double *)c->tmp_in.p;
-            }
-            dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((inner + 31) / 32));
-            k_transpose<<<grid, dim3(32, 8), 0, c->stream>>>(dsrc, (double *)dst.p, inner, batch);
-            c->launches++;
-            FTSB_CUDA(c, cudaGetLastError());
-            if (mem == FTSB_MEM_HOST) FTSB_CUDA(c, cudaStreamSynchronize(c->stream)); // tmp_in is reused
-        }
+        FTSB_CUDA(c, cudaMemcpyAsync(dst.p, src, (size_t)batch * inner * 8, kind, c->stream));
         return 0;
     };
     int rc = put(c->vals, vals, ne);
@@ -1214,6 +1232,17 @@ int ftsb_set_params(ftsb_circuit *c, int64_t batch, const double *vals, const do
     if (rc) return rc;
     if (mem == FTSB_MEM_HOST) FTSB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->batch = batch;
+    if (layout == FTSB_LAYOUT_INSTANCE_MAJOR) {
+        c->vs_inst = ne;
+        c->vs_elem = 1;
+        c->fs_inst = (long long)nf * 7;
+        c->fs_elem = 1;
+    } else {
+        c->vs_inst = 1;
+        c->vs_elem = batch;
+        c->fs_inst = 1;
+        c->fs_elem = batch;
+    }
     return 0;
 }
 
@@ -1396,8 +1425,16 @@ int solve_pipelined_impl(ftsb_circuit *c, int an, long long B, const PipeIo &io,
         FTSB_CUDA(c, c->o_done.ensure((size_t)B * 8));
     }
     c->batch = B;
+    c->vs_inst = ne;
+    c->vs_elem = 1;
+    c->fs_inst = (long long)nf * 7;
+    c->fs_elem = 1;
     RunArgs a{};
     a.prog = c->prog;
+    a.vs_inst = c->vs_inst;
+    a.vs_elem = c->vs_elem;
+    a.fs_inst = c->fs_inst;
+    a.fs_elem = c->fs_elem;
     a.batch = B;
     a.vals = (const double *)c->vals.p;
     a.fn = (const double *)c->fn.p;

@@ -39,8 +39,9 @@ enum : int { CN_POINTS = 0, CN_NEWTON = 1, CN_FACTOR = 2, CN_SOLVE = 3, CN_REJ_N
 struct RunArgs {
     DevProg prog;
     long long batch;
-    const double *vals; // [batch][n_elems]
-    const double *fn;   // [batch][n_fn][7]
+    const double *vals; // element e of instance i at vals[i * vs_inst + e * vs_elem]: [batch][n_elems] or [n_elems][batch]
+    const double *fn;   // word k (= fn_slot * 7 + field) of instance i at fn[i * fs_inst + k * fs_elem]
+    long long vs_inst, vs_elem, fs_inst, fs_elem; // no transposition on the way in: the kernels read either layout in place
     unsigned long long *work; // atomic work counter
     unsigned long long *counters; // [CN_COUNT]
     double *scratch;    // global A/J storage when the matrices do not fit in shared memory
@@ -280,7 +281,18 @@ __device__ __forceinline__ void gather(const Team &tm, const Gather &g, V out, V
 // ---------------------------------------------------------------------------------------------------------
 // source waveforms  (src/spice_fn.rs:8-124)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double spice_fn_eval(int kind, const double *p, double t)
+// strided read-only view of one instance's parameters (instance-major: stride 1; parameter-major: stride = batch)
+struct ParamView {
+    const double *p;
+    long long se;
+    __device__ __forceinline__ double operator[](int e) const { return p[e * se]; }
+    __device__ __forceinline__ ParamView operator+(int off) const { return ParamView{p + off * se, se}; }
+};
+__device__ __forceinline__ ParamView vals_of(const RunArgs &a, long long inst) { return ParamView{a.vals + inst * a.vs_inst, a.vs_elem}; }
+__device__ __forceinline__ ParamView fns_of(const RunArgs &a, long long inst) { return ParamView{a.fn + inst * a.fs_inst, a.fs_elem}; }
+
+template <class PV>
+__device__ __forceinline__ double spice_fn_eval(int kind, PV p, double t)
 {
     if (kind == FN_SIN) {
         return p[0] + p[1] * sin(2.0 * 3.14159265358979323846 * p[2] * t);
@@ -691,8 +703,7 @@ template <class Team, class W>
 __device__ __forceinline__ void load_instance(const Team &tm, const RunArgs &a, const W &w, long long inst)
 {
     const DevProg &P = a.prog;
-    const double *vals = a.vals + inst * P.n_elems;
-    const double *fn = a.fn + inst * (long long)P.n_fn * 7;
+    const ParamView vals = vals_of(a, inst), fn = fns_of(a, inst);
     if (tm.rank == 0) w.val[SLOT_ONE] = 1.0;
     for (int i = tm.rank; i < P.n_res; i += tm.size()) {
         int e = __ldg(&P.res[2 * i]), s = __ldg(&P.res[2 * i + 1]);
@@ -818,8 +829,7 @@ __device__ __forceinline__ void run_tran_instance(const Team &tm, const RunArgs 
     const DevProg &P = a.prog;
     const ModeProg &M = P.tran;
     const int n = M.n, ld = w.ld;
-    const double *vals = a.vals + inst * P.n_elems;
-    const double *fn = a.fn + inst * (long long)P.n_fn * 7;
+    const ParamView vals = vals_of(a, inst), fn = fns_of(a, inst);
 
     load_instance(tm, a, w, inst);
     long long nrec = 0, stored = 0;

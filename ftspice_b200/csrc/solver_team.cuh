@@ -480,8 +480,7 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
             if (!__any_sync(0xffffffffu, have)) break;
             if (__any_sync(0xffffffffu, fresh)) {
                 if (fresh) { // load_instance (engine.cuh) + start-up solution + init_state (cap.rs:38-47, ind.rs:42-49)
-                    const double *vals = a.vals + inst * DP.n_elems;
-                    const double *fn = a.fn + inst * (long long)DP.n_fn * 7;
+                    const ParamView vals = vals_of(a, inst), fn = fns_of(a, inst);
                     if (l == 0) val[SLOT_ONE] = 1.0;
                     for (int i = l; i < DP.n_res; i += G) {
                         const int e = __ldg(&DP.res[2 * i]), s = __ldg(&DP.res[2 * i + 1]);
@@ -550,7 +549,7 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
             }
             const double te = t + h;
             if (act) { // time-varying sources at t + h (transient.rs:36-42); I sources drift (quirk Q9)
-                const double *fn = a.fn + inst * (long long)DP.n_fn * 7;
+                const ParamView fn = fns_of(a, inst);
                 for (int i = l; i < DP.n_src; i += G) {
                     const int *sd = &DP.src[5 * i];
                     const int s = __ldg(&sd[1]), kind = __ldg(&sd[2]), fk = __ldg(&sd[3]), fs = __ldg(&sd[4]);

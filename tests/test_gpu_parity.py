@@ -302,6 +302,43 @@ def test_param_major_layout_and_device_buffers():
     assert np.array_equal(st.cpu().numpy(), ref.status)
 
 
+@pytest.mark.parametrize("which,B", [("proj1_nl", 20000), ("ladder24", 40)])
+def test_param_major_is_read_in_place_by_every_kernel_family(which, B):
+    """FTSB_LAYOUT_PARAM_MAJOR input (vals[elem][instance], fn[slot][7][instance]) is not transposed: the kernels read it
+    with strides — the per-topology kernel (one thread per instance: coalesced 256-byte requests per element), the plan
+    and dense small-circuit kernels, the per-team / warp .tran kernels — and give the bits of the instance-major run."""
+    import ctypes as ct
+    circ = nl.load(nl.PROJ1_NL) if which == "proj1_nl" else nl.load(
+        nl.ladder_netlist(24, "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )", stop="30n", step="1n"))
+    vals, fns = nl.monte_carlo(circ, B, rel=0.3 if which == "proj1_nl" else 0.1)
+    tran = circ.command("tran")
+    outs = []
+    for layout in (capi.LAYOUT_INSTANCE_MAJOR, capi.LAYOUT_PARAM_MAJOR):
+        be = BatchEngine(circ)
+        f = be.compact_fns(fns) if be.n_fn else None
+        if layout == capi.LAYOUT_PARAM_MAJOR:
+            v = np.ascontiguousarray(vals.T)
+            f = np.ascontiguousarray(f.transpose(1, 2, 0)) if f is not None else None
+        else:
+            v = np.ascontiguousarray(vals)
+        res = []
+        for rep in range(3):  # the third .op call of a handle runs the per-topology kernel
+            capi.check(capi.lib().ftsb_set_params(be.h, B, v.ctypes.data_as(ct.c_void_p), f.ctypes.data_as(ct.c_void_p) if f is not None
+                                                  else None, layout, capi.MEM_HOST), be.h)
+            be.batch = B
+            if tran:
+                r = be.run_tran(tran.stop, tran.step, capacity=300)
+                res = (be.variant, r.status, r.n_rec, r.n_iters, r.t, r.x, r.x_final)
+                break
+            r = be.run_op()
+            res = (be.variant, r.status, r.n_iters, r.x)
+        outs.append(res)
+    assert outs[0][0].split("/")[0] == outs[1][0].split("/")[0], (outs[0][0], outs[1][0])
+    assert outs[0][0].startswith("team" if tran else "jit"), outs[0][0]
+    for a_, b_ in zip(outs[0][1:], outs[1][1:]):
+        assert np.array_equal(a_, b_, equal_nan=True)
+
+
 def test_api_errors():
     circ = load("v_divider")
     be = BatchEngine(circ)
