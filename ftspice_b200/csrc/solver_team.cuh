@@ -278,7 +278,7 @@ struct TeamOps {
     // forward: y through the stored multipliers (gauss_lu.rs:40)
     static __device__ void chain_forward(const TeamPlan &P, V sva, V y, V stg, int l, bool on)
     {
-        constexpr int VPL = TEAM_CHUNK / G;
+        constexpr int VPL = TEAM_CHUNK / G > 0 ? TEAM_CHUNK / G : 1; // (G <= TEAM_CHUNK: the kernel does not use the streams otherwise)
         double vreg[VPL];
         const int nchunk = P.nFchunk;
 #pragma unroll
@@ -325,7 +325,7 @@ struct TeamOps {
     // backward: gauss_lu.rs:44-53; false when a solution component is not finite
     static __device__ bool chain_backward(const TeamPlan &P, V sva, V y, V xp, V stg, int l, bool on, unsigned tmask)
     {
-        constexpr int VPL = TEAM_CHUNK / G;
+        constexpr int VPL = TEAM_CHUNK / G > 0 ? TEAM_CHUNK / G : 1;
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         double vreg[VPL];
         const int nchunk = P.nBchunk;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
     const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T};
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const bool linear = M.n_nl == 0;
-    const bool chain = P.chain != 0;
+    const bool chain = P.chain != 0 && G <= TEAM_CHUNK; // single-lane op streams (ladders); wider teams: lane-parallel lists
     const int R = (n + G - 1) / G; // rows per lane: row i = j * G + l, j < R
     unsigned clsmask = 0;          // bit j: row j * G + l is a current row (NodeType::Current); R <= 32 (launcher)
     for (int j = 0; j < R && j < 32; ++j) {

@@ -59,7 +59,7 @@ struct TeamPlan {
     const int *bchunk;      // [nBchunk + 1]
 };
 
-constexpr int TEAM_CHUNK = 32;
+constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
 
 struct TeamPlanHost {
     int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0;

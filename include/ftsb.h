@@ -65,8 +65,10 @@ enum {
 /* where the caller's buffers live */
 enum {
     FTSB_MEM_HOST = 0,  /* host pointers; the call copies in/out and returns when results are in place */
-    FTSB_MEM_DEVICE = 1 /* device pointers on the handle's device; the call only enqueues work on the
-                           handle's stream and returns; use ftsb_sync().  Exception: the first .op / .dc calls
+    FTSB_MEM_DEVICE = 1 /* pointers the handle's device can dereference — device memory, or page-locked host memory
+                           (unified addressing): with the latter .tran records STREAM into host memory while the
+                           kernel runs, which is how waveforms larger than HBM leave the GPU; the call only enqueues
+                           work on the handle's stream and returns; use ftsb_sync().  Exception: the first .op / .dc calls
                            of a handle on a small circuit learn elimination plans from a pilot run and compile
                            a per-topology kernel (about a second, once); those calls synchronise the stream */
 };

@@ -261,6 +261,36 @@ def test_tran_record_stride(oracle_mod):
     assert np.array_equal(none.x_final, full.x_final)
 
 
+def test_tran_streams_records_into_page_locked_host_memory():
+    """Waveform streaming: with FTSB_MEM_DEVICE the output pointers may be any device-accessible memory, including
+    page-locked HOST buffers (unified addressing): the kernel then writes every accepted record (state_history.rs:24-30)
+    straight into host memory while it runs — no device-side waveform buffer, no copy afterwards.  Same bits as the staged
+    host path."""
+    import torch
+    circ = nl.load(nl.ladder_netlist(24, "PULSE( 0.0 1.0 0.0 10n 10n 50n 100n )", stop="40n", step="1n"))
+    B, cap, n = 9, 300, circ.n_run
+    vals, fns = nl.monte_carlo(circ, B)
+    tr = circ.command("tran")
+    be = BatchEngine(circ)
+    be.set_params(vals, fns)
+    ref = be.run_tran(tr.stop, tr.step, capacity=cap)
+    t = torch.zeros((B, cap), dtype=torch.float64).pin_memory()
+    x = torch.zeros((B, cap, n), dtype=torch.float64).pin_memory()
+    it = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
+    nrec = torch.zeros(B, dtype=torch.int64).pin_memory()
+    xf = torch.zeros((B, n), dtype=torch.float64).pin_memory()
+    st = torch.zeros(B, dtype=torch.int32).pin_memory()
+    be.run_tran_device(tr.stop, tr.step, cap, 1, t.data_ptr(), x.data_ptr(), it.data_ptr(), nrec.data_ptr(), xf.data_ptr(),
+                       st.data_ptr())
+    be.sync()
+    assert np.array_equal(nrec.numpy(), ref.n_rec) and np.array_equal(st.numpy(), ref.status)
+    for i in range(B):
+        k = int(ref.n_rec[i])
+        assert np.array_equal(t.numpy()[i, :k], ref.t[i, :k]) and np.array_equal(x.numpy()[i, :k], ref.x[i, :k])
+        assert np.array_equal(it.numpy()[i, :k], ref.n_iters[i, :k])
+    assert np.array_equal(xf.numpy(), ref.x_final)
+
+
 def test_tran_inverter_chain_small(oracle_mod):
     """C5 shape at reduced size: NMOS inverter chain (CTA path), nonlinear + dynamic."""
     circ = nl.load(nl.inverter_chain_netlist(40, stop="3n", step="50p"))

@@ -12,6 +12,8 @@ from ftspice_b200 import netlist as nl
 
 from test_q9_isource import mid_netlist
 
+CHUNK = 8  # TEAM_CHUNK of team_plan.h
+
 CIRCUITS = {
     "ladder64": lambda: nl.ladder_netlist(64, "SIN( 0.0 1.0 10M )", stop="40n", step="1n"),
     "ladder24_isrc": lambda: mid_netlist(24),
@@ -54,8 +56,8 @@ def team_plan(circ, an=2):
             p[k] = ibuf[int(o):int(o) + lens[k]].copy()
     for k, v in zip(["ellW", "nSlotA", "chain", "nFop", "nBop", "nFchunk", "nBchunk"], meta[25:32]):
         p[k] = int(v)
-    lens2 = {"fop": p["nFop"], "fvidx": p["nFchunk"] * 32, "fchunk": p["nFchunk"] + 1, "bop": 2 * p["nBop"],
-             "bvidx": p["nBchunk"] * 32, "bchunk": p["nBchunk"] + 1, "ellcol": 2 * (p["n"] + 1), "ovfptr": p["n"] + 1}
+    lens2 = {"fop": p["nFop"], "fvidx": p["nFchunk"] * CHUNK, "fchunk": p["nFchunk"] + 1, "bop": 2 * p["nBop"],
+             "bvidx": p["nBchunk"] * CHUNK, "bchunk": p["nBchunk"] + 1, "ellcol": 2 * (p["n"] + 1), "ovfptr": p["n"] + 1}
     for k, o in zip(["fop", "fvidx", "fchunk", "bop", "bvidx", "bchunk", "ellcol", "ovfptr", "ovfcol"], meta[32:41]):
         if k in lens2:
             p[k] = ibuf[int(o):int(o) + lens2[k]].copy()
@@ -67,12 +69,12 @@ def team_plan(circ, an=2):
 
 
 def run_streams(p, sv, alpha, rhs):
-    """The kernel's chain_forward / chain_backward: op streams, values staged in chunks of 32 slots."""
+    """The kernel's chain_forward / chain_backward: op streams, values staged in chunks of CHUNK slots."""
     n, S = p["n"], p["S"]
     sva = np.concatenate([sv, alpha])
     y = rhs.copy()
     for c in range(p["nFchunk"]):
-        buf = sva[p["fvidx"][32 * c:32 * c + 32]]
+        buf = sva[p["fvidx"][CHUNK * c:CHUNK * c + CHUNK]]
         slot = 0
         for op in range(p["fchunk"][c], p["fchunk"][c + 1]):
             w0 = int(p["fop"][op])
@@ -84,7 +86,7 @@ def run_streams(p, sv, alpha, rhs):
     x = np.full(n, np.nan)
     xi = 0.0
     for c in range(p["nBchunk"]):
-        buf = sva[p["bvidx"][32 * c:32 * c + 32]]
+        buf = sva[p["bvidx"][CHUNK * c:CHUNK * c + CHUNK]]
         slot = 0
         for op in range(p["bchunk"][c], p["bchunk"][c + 1]):
             w0, w1 = int(p["bop"][2 * op]), int(p["bop"][2 * op + 1])
@@ -98,7 +100,7 @@ def run_streams(p, sv, alpha, rhs):
             else:
                 y[w0] = y[w0] - xi * buf[slot]
                 slot += 1
-        assert slot <= 32
+        assert slot <= CHUNK
     assert p["fchunk"][-1] == p["nFop"] and p["bchunk"][-1] == p["nBop"]
     return x
 
