@@ -792,12 +792,21 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     if (c->team_state != 1) return 1;
     const TeamPlanHost &ph = c->team_plan;
     const bool linear = mo.n_nl == 0;
-    const int place = c->team_place >= 0 ? (c->team_place & 3) : (linear ? 0 : 3);
+    // placement: a linear circuit touches its slot table and factors once per attempt (global scratch); a nonlinear one in
+    // every Newton iteration (shared memory).  A circuit too large for that (n = 258: 54 KB per instance) can run with
+    // only the factors and the vectors in shared memory (option team_place = 6: slot table and entries of A in the
+    // scratch, elimination as early steps + one op stream) — measured SLOWER than the warp kernel's windowed elimination
+    // on the C5 chain (0.22 vs 0.28 M solve-points/s on 4 096 instances x 4 ns: one lane walks ~1 550 dependent ops per
+    // Newton iteration), so it is not chosen automatically
+    int place = 0;
     // lanes per instance: rows are dealt round-robin, so few lanes waste little; more teams per warp amortise the
     // list-walking code over more instances but need more shared memory per warp
     int best_g = 0, best_occ = 0, best_wpb = 0;
     size_t best_smem = 0;
     TeamLayout best_lay{};
+    for (int place_try : {c->team_place >= 0 ? (c->team_place & 7) : (linear ? 0 : 3), -1}) {
+    if (place_try < 0 || best_g) break;
+    place = place_try;
     for (int g : {8, 16, 32}) {
         if (c->team_g > 0) g = c->team_g;
         TeamKernelFn fn = (mo.n + g - 1) / g <= 32 ? team_kernel(g, place, ph.ellW) : nullptr; // rows per lane fit a 32-bit class mask
@@ -831,6 +840,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
             }
         }
         if (c->team_g > 0 || best_g) break;
+    }
     }
     if (!best_g) return 1;
     const int T = 32 / best_g;
@@ -1943,6 +1953,8 @@ extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int
     const int m2[] = {ph.ellW, ph.nSlotA, ph.chain, ph.nFop, ph.nBop, ph.nFchunk, ph.nBchunk, ph.o_fop, ph.o_fvidx, ph.o_fchunk,
                       ph.o_bop, ph.o_bvidx, ph.o_bchunk, ph.o_ellcol, ph.o_ovfptr, ph.o_ovfcol};
     std::copy(m2, m2 + 16, meta + 25); // meta[25..40]
+    const int m3[] = {ph.nEarly, ph.nXop, ph.nDFop, ph.nDBop, ph.o_early, ph.o_xop, ph.o_dfop, ph.o_dbop};
+    std::copy(m3, m3 + 8, meta + 41); // meta[41..48]: the direct streams
     for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
     std::copy(pv.begin(), pv.end(), piv);
     return 0;

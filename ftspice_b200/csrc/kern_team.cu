@@ -22,13 +22,15 @@ static TeamKernelFn pick(int g)
 TeamKernelFn team_kernel(int g, int place, int ell_w)
 {
     if (ell_w != 3 && ell_w != 4) return nullptr;
-    switch (place & 3) {
+    switch (place) {
     case 0:
         return ell_w == 3 ? pick<0, 3>(g) : pick<0, 4>(g);
     case 1:
         return ell_w == 3 ? pick<1, 3>(g) : pick<1, 4>(g);
     case 3:
         return ell_w == 3 ? pick<3, 3>(g) : pick<3, 4>(g);
+    case 6: // large nonlinear circuits: factors in shared memory, slot table and the entries of A in the global region
+        return ell_w == 3 ? pick<6, 3>(g) : pick<6, 4>(g);
     default:
         return nullptr;
     }

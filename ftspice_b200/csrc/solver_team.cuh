@@ -39,7 +39,7 @@ struct TeamLayout {
 };
 
 // place: bit 0 = slot table in shared memory, bit 1 = factors in shared memory (nonlinear circuits: both are touched in
-// every Newton iteration)
+// every Newton iteration), bit 2 = the entries of A in the global region (large circuits: read once per iteration)
 __host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_slots, int n_dyn, int n_src, int place)
 {
     TeamLayout t;
@@ -58,7 +58,7 @@ __host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_sl
     t.oxp = ts(n + 1);
     t.ob = ts(n + 1);
     t.oy = ts(n);
-    t.oA = ts(nA);
+    t.oA = (place & 4) ? tg(nA) : ts(nA);
     t.oprev = ts(3 * n_src);
     t.ostg = ts(2 * TEAM_CHUNK);
     t.oval = (place & 1) ? ts(n_slots) : tg(n_slots);
@@ -133,15 +133,34 @@ struct TeamOps {
     static __device__ __forceinline__ void assemble_sv(const TeamPlan &P, V val, V sv, int l, bool on)
     {
         if (on) {
-            for (int e = l; e < P.nJ; e += G) {
-                double acc = 0.0;
-                const int c0 = __ldg(&P.sptr[e]), c1 = __ldg(&P.sptr[e + 1]);
-                for (int c = c0; c < c1; ++c) {
-                    const unsigned wd = (unsigned)__ldg(&P.scon[c]);
-                    const double v = val[wd & ~CON_NEG];
-                    acc += (wd & CON_NEG) ? -v : v;
+            constexpr int EB = 4; // entries in flight per lane (the slot table may live in L2: overlap the gathers)
+            for (int e0 = l; e0 < P.nJ; e0 += EB * G) {
+                int c0[EB], len[EB], maxlen = 0;
+                double acc[EB];
+#pragma unroll
+                for (int u = 0; u < EB; ++u) {
+                    const int e = e0 + u * G;
+                    const bool oke = e < P.nJ;
+                    c0[u] = oke ? __ldg(&P.sptr[e]) : 0;
+                    len[u] = oke ? __ldg(&P.sptr[e + 1]) - c0[u] : 0;
+                    maxlen = max(maxlen, len[u]);
+                    acc[u] = 0.0;
                 }
-                sv[e] = acc;
+                for (int tt = 0; tt < maxlen; ++tt) {
+#pragma unroll
+                    for (int u = 0; u < EB; ++u) {
+                        if (tt < len[u]) {
+                            const unsigned wd = (unsigned)__ldg(&P.scon[c0[u] + tt]);
+                            const double v = val[wd & ~CON_NEG];
+                            acc[u] += (wd & CON_NEG) ? -v : v;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < EB; ++u) {
+                    const int e = e0 + u * G;
+                    if (e < P.nJ) sv[e] = acc[u];
+                }
             }
             for (int e = P.nJ + l; e < P.S; e += G) sv[e] = 0.0;
         }
@@ -381,6 +400,129 @@ struct TeamOps {
         return !any(bad, tmask);
     }
 
+    // ---- direct streams (team_plan.h): the factors live in shared memory, one lane walks the ops, no staging ----
+    // pivot check, reciprocal and multipliers of elimination step k (gauss_lu.rs:6-32); returns true when the planned row
+    // is not the reference's pivot or a candidate is zero-only / infinite / NaN
+    static __device__ __forceinline__ bool step_head(const TeamPlan &P, V sv, V alpha, int k)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        const int t0 = __ldg(&P.tptr[k]), t1 = __ldg(&P.tptr[k + 1]);
+        const double ap = sv[__ldg(&P.pive[k])];
+        const double abs_p = fabs(ap);
+        bool bad = !(abs_p > 0.0 && abs_p < INF);
+        const double al = 1.0 / ap; // (:31)
+        alpha[k] = al;
+        for (int tt = t0; tt < t1; ++tt) {
+            const int w = __ldg(&P.tgt[tt]);
+            const int e = w & 0xffff;
+            const double a = sv[e];
+            const double av = fabs(a);
+            bad |= (w >> 30) ? !(av < abs_p) : !(av <= abs_p);
+            sv[e] = al * a; // (:32)
+        }
+        return bad;
+    }
+    static __device__ bool factor_direct(const TeamPlan &P, V sv, V alpha, int l, bool on, unsigned tmask)
+    {
+        bool bad = false;
+        for (int idx = l; idx < P.nEarly; idx += G) { // steps no earlier update reaches: all at once, lanes in parallel
+            const int k = __ldg(&P.early[idx]);
+            if (on) bad |= step_head(P, sv, alpha, k);
+        }
+        __syncwarp();
+        if (on && l == 0) { // the rest, in elimination order
+            const int nop = P.nXop;
+            const int2 *ops = reinterpret_cast<const int2 *>(P.xop);
+            for (int o0 = 0; o0 < nop; o0 += 8) {
+                int2 w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = o0 + k < nop ? __ldg(ops + o0 + k) : make_int2(0, 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (o0 + k < nop) {
+                        if (w[k].y < 0)
+                            bad |= step_head(P, sv, alpha, w[k].x);
+                        else {
+                            const double m = sv[w[k].y];
+                            if (m != 0.0) { // a - 0 * p == a
+                                const int d = w[k].x & 0xffff, s_ = (w[k].x >> 16) & 0xffff;
+                                sv[d] = sv[d] - m * sv[s_]; // (:35-39)
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        return any(on && bad, tmask);
+    }
+    static __device__ void forward_direct(const TeamPlan &P, V sv, V y, int l, bool on)
+    {
+        if (on && l == 0) {
+            const int nop = P.nDFop;
+            const int2 *ops = reinterpret_cast<const int2 *>(P.dfop);
+            double last_v = 0.0;
+            int last_r = -1;
+            for (int o0 = 0; o0 < nop; o0 += 8) {
+                int2 w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = o0 + k < nop ? __ldg(ops + o0 + k) : make_int2(0, 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (o0 + k < nop) {
+                        const double m = sv[w[k].y];
+                        if (m != 0.0) {
+                            const int r = w[k].x & 0xffff, pk = (w[k].x >> 16) & 0xffff;
+                            const double ypk = pk == last_r ? last_v : y[pk];
+                            const double yr = r == last_r ? last_v : y[r];
+                            const double v = yr - m * ypk; // (:40)
+                            y[r] = v;
+                            last_r = r;
+                            last_v = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    static __device__ bool backward_direct(const TeamPlan &P, V sv, V alpha, V y, V xp, int l, bool on, unsigned tmask)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        bool bad = false;
+        if (on && l == 0) {
+            const int nop = P.nDBop;
+            const int2 *ops = reinterpret_cast<const int2 *>(P.dbop);
+            double last_v = 0.0, xi = 0.0;
+            int last_r = -1;
+            for (int o0 = 0; o0 < nop; o0 += 8) {
+                int2 w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = o0 + k < nop ? __ldg(ops + o0 + k) : make_int2(0, 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (o0 + k < nop) {
+                        const int row = w[k].x & 0xffff;
+                        const double yv = row == last_r ? last_v : y[row];
+                        if (w[k].y < 0) { // x_i = y[pivot row] / pivot (gauss_lu.rs:47)
+                            const int i = (w[k].x >> 16) & 0xffff;
+                            xi = div_known_rcp(yv, sv[w[k].y & 0xffff], alpha[i]);
+                            xp[i] = xi;
+                            bad |= !(fabs(xi) < INF);
+                        } else { // y[r] -= x_i * u(r, i) (:49-52)
+                            const double v = yv - xi * sv[w[k].y];
+                            y[row] = v;
+                            last_r = row;
+                            last_v = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        return !any(bad, tmask);
+    }
+
     // nonlinear devices at x -> slot values; returns team-wide (#non-finite currents) | panic << 20
     static __device__ __forceinline__ int eval_nl(const ModeProg &M, V x, V val, int l, bool on)
     {
@@ -422,7 +564,7 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
     const unsigned tmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
     double *sw = tab + 2 * FTS_LOG1P_N + (size_t)warp * L.sm_doubles * T + q;
     double *gw = ta.gscratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)L.gl_doubles * T + q;
-    const V x{sw + L.ox * T}, xp{sw + L.oxp * T}, b{sw + L.ob * T}, y{sw + L.oy * T}, A{sw + L.oA * T}, prev{sw + L.oprev * T};
+    const V x{sw + L.ox * T}, xp{sw + L.oxp * T}, b{sw + L.ob * T}, y{sw + L.oy * T}, A{((PLACE & 4) ? gw : sw) + L.oA * T}, prev{sw + L.oprev * T};
     const V stg{sw + L.ostg * T};
     const V val{((PLACE & 1) ? sw : gw) + L.oval * T};
     const V sv{((PLACE & 2) ? sw : gw) + L.osv * T}, alpha{((PLACE & 2) ? sw : gw) + L.oalpha * T};
@@ -620,13 +762,19 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
                         for (int i = l; i < n; i += G) y[i] = Ops::gsum(M.r_nl, i, val, b[i]);
                     Ops::assemble_sv(P, val, sv, l, it_on);
                     __syncwarp();
-                    if (Ops::factor(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
-                    if (chain) {
-                        Ops::chain_forward(P, sv, y, stg, l, it_on);
-                        if (!Ops::chain_backward(P, sv, y, xp, stg, l, it_on, tmask) && it_on) redo = true;
+                    if constexpr ((PLACE & 2) != 0) { // factors in shared memory: early steps in parallel, then one op stream
+                        if (Ops::factor_direct(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                        Ops::forward_direct(P, sv, y, l, it_on);
+                        if (!Ops::backward_direct(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
                     } else {
-                        Ops::forward(P, sv, y, l, it_on);
-                        if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                        if (Ops::factor(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                        if (chain) {
+                            Ops::chain_forward(P, sv, y, stg, l, it_on);
+                            if (!Ops::chain_backward(P, sv, y, xp, stg, l, it_on, tmask) && it_on) redo = true;
+                        } else {
+                            Ops::forward(P, sv, y, l, it_on);
+                            if (!Ops::backward(P, sv, alpha, y, xp, l, it_on) && it_on) redo = true;
+                        }
                     }
                     if (it_on) {
                         ci[CN_FACTOR]++;

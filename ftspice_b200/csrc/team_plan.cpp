@@ -46,6 +46,14 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.bop = b + o_bop;
     p.bvidx = b + o_bvidx;
     p.bchunk = b + o_bchunk;
+    p.nEarly = nEarly;
+    p.nXop = nXop;
+    p.nDFop = nDFop;
+    p.nDBop = nDBop;
+    p.early = b + o_early;
+    p.xop = b + o_xop;
+    p.dfop = b + o_dfop;
+    p.dbop = b + o_dbop;
     return p;
 }
 
@@ -236,6 +244,46 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
         out.o_bop = push2(bop);
         out.o_bvidx = push2(bvidx);
         out.o_bchunk = push2(bchunk);
+        // ---- direct streams (factors in shared memory) ----
+        {
+            std::vector<char> written(S, 0); // entries some update of an EARLIER step writes
+            std::vector<int> early, xop, dfop, dbop;
+            for (int k = 0; k < n; ++k) {
+                bool is_early = !written[pive[k]];
+                for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) is_early = is_early && !written[tgt[tt] & 0xffff];
+                if (is_early)
+                    early.push_back(k);
+                else {
+                    xop.push_back(k);
+                    xop.push_back((int)0x80000000u);
+                }
+                for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) {
+                    for (int u = uptr[tt]; u < uptr[tt + 1]; ++u) {
+                        xop.push_back(updds[u]);
+                        xop.push_back(updm[u]);
+                        written[updds[u] & 0xffff] = 1;
+                    }
+                    dfop.push_back(tgtr[tt] | (pivrow[k] << 16));
+                    dfop.push_back(tgt[tt] & 0xffff);
+                }
+            }
+            for (int i = n - 1; i >= 0; --i) {
+                dbop.push_back(pivrow[i] | (i << 16));
+                dbop.push_back((int)(0x80000000u | (unsigned)pive[i]));
+                for (int bb = bptr[i]; bb < bptr[i + 1]; ++bb) {
+                    dbop.push_back(bwdr[bb]);
+                    dbop.push_back(bwde[bb]);
+                }
+            }
+            out.nEarly = (int)early.size();
+            out.nXop = (int)xop.size() / 2;
+            out.nDFop = (int)dfop.size() / 2;
+            out.nDBop = (int)dbop.size() / 2;
+            out.o_early = push2(early);
+            out.o_xop = push2(xop);
+            out.o_dfop = push2(dfop);
+            out.o_dbop = push2(dbop);
+        }
         out.o_ellcol = push2(ellcol);
         out.o_ovfptr = push2(ovfptr);
         out.o_ovfcol = push2(ovfcol);

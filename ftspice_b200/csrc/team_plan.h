@@ -57,6 +57,19 @@ struct TeamPlan {
     const int *bop;         // [nBop][2]
     const int *bvidx;       // [nBchunk * TEAM_CHUNK]
     const int *bchunk;      // [nBchunk + 1]
+    // ---- direct streams, for factors that live in shared memory (nonlinear circuits: a factorisation per Newton
+    //      iteration).  An elimination step whose pivot and column entries no earlier update writes is EARLY: its pivot
+    //      check, reciprocal and multipliers are done for all such steps at once, lanes in parallel (an inverter chain:
+    //      every stage); what is left — the other steps' checks / multipliers inline, and every `sv[d] -= sv[m] * sv[s]`
+    //      update in elimination order (the rail column of a chain is a true recurrence) — is one op stream walked by one
+    //      lane.  xop: word1 < 0: inline step, word0 = k; else update, word0 = dst | src << 16, word1 = multiplier entry.
+    //      dfop: word0 = row r | pivot row << 16, word1 = multiplier entry.  dbop: word1 < 0: divide, word0 = pivot row |
+    //      column i << 16, word1 & 0xffff = pivot entry; else update, word0 = row r, word1 = entry of U.
+    int nEarly, nXop, nDFop, nDBop;
+    const int *early;       // [nEarly] step indices
+    const int *xop;         // [nXop][2]
+    const int *dfop;        // [nDFop][2]
+    const int *dbop;        // [nDBop][2]
 };
 
 constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
@@ -69,6 +82,7 @@ struct TeamPlanHost {
     int ellW = 0, nSlotA = 0, o_ellcol = 0, o_ovfptr = 0, o_ovfcol = 0;
     int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,
         o_bchunk = 0;
+    int nEarly = 0, nXop = 0, nDFop = 0, nDBop = 0, o_early = 0, o_xop = 0, o_dfop = 0, o_dbop = 0;
     long long flops_factor = 0, flops_solve = 0; // floating-point operations of one factorisation / one pair of substitutions
     TeamPlan view(const int *base) const;
 };

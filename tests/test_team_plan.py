@@ -63,6 +63,10 @@ def team_plan(circ, an=2):
             p[k] = ibuf[int(o):int(o) + lens2[k]].copy()
         else:
             p[k] = ibuf[int(o):int(o) + int(p["ovfptr"][-1])].copy()
+    for k, v in zip(["nEarly", "nXop", "nDFop", "nDBop"], meta[41:45]):
+        p[k] = int(v)
+    for k, o, ln in zip(["early", "xop", "dfop", "dbop"], meta[45:49], [p["nEarly"], 2 * p["nXop"], 2 * p["nDFop"], 2 * p["nDBop"]]):
+        p[k] = ibuf[int(o):int(o) + ln].copy()
     p["jdst"] = jdst[:p["nJ"]].copy()
     p["piv"] = piv[:p["n"]].copy()
     return p
@@ -102,6 +106,51 @@ def run_streams(p, sv, alpha, rhs):
                 slot += 1
         assert slot <= CHUNK
     assert p["fchunk"][-1] == p["nFop"] and p["bchunk"][-1] == p["nBop"]
+    return x
+
+
+def run_direct(p, vals, rhs):
+    """factor_direct / forward_direct / backward_direct of solver_team.cuh: early steps first (any order), then the op stream."""
+    n, S = p["n"], p["S"]
+    sv = np.zeros(S)
+    sv[:p["nJ"]] = vals
+    alpha = np.zeros(n)
+
+    def head(k):
+        al = np.float64(1.0) / sv[p["pive"][k]]
+        alpha[k] = al
+        for tt in range(p["tptr"][k], p["tptr"][k + 1]):
+            e = p["tgt"][tt] & 0xffff
+            sv[e] = al * sv[e]
+
+    for k in reversed(p["early"].tolist()):  # the kernel does them lanes-in-parallel: order must not matter
+        head(k)
+    for op in range(p["nXop"]):
+        w0, w1 = int(p["xop"][2 * op]), int(p["xop"][2 * op + 1])
+        if w1 < 0:
+            head(w0)
+        else:
+            m = sv[w1]
+            if m != 0.0:
+                d, s = w0 & 0xffff, (w0 >> 16) & 0xffff
+                sv[d] = sv[d] - m * sv[s]
+    y = rhs.copy()
+    for op in range(p["nDFop"]):
+        w0, w1 = int(p["dfop"][2 * op]), int(p["dfop"][2 * op + 1])
+        m = sv[w1]
+        if m != 0.0:
+            r, pk = w0 & 0xffff, (w0 >> 16) & 0xffff
+            y[r] = y[r] - m * y[pk]
+    x = np.full(n, np.nan)
+    xi = 0.0
+    for op in range(p["nDBop"]):
+        w0, w1 = int(p["dbop"][2 * op]), int(p["dbop"][2 * op + 1])
+        if w1 < 0:
+            pi, i = w0 & 0xffff, (w0 >> 16) & 0xffff
+            xi = y[pi] / sv[w1 & 0xffff]
+            x[i] = xi
+        else:
+            y[w0] = y[w0] - xi * sv[w1]
     return x
 
 
@@ -190,6 +239,7 @@ def test_plan_equals_dense_elimination_bitwise(which):
         assert np.all(np.isfinite(x_dense))
         assert np.array_equal(x_plan, x_dense), (which, trial, np.abs(x_plan - x_dense).max())
         assert np.array_equal(run_plan(p, vals, rhs, streams=True), x_dense), (which, trial, "op streams")
+        assert np.array_equal(run_direct(p, vals, rhs), x_dense), (which, trial, "direct streams")
         assert np.abs(a @ x_plan - rhs).max() < 1e-6 * max(1.0, np.abs(x_plan).max())
 
 
@@ -217,6 +267,9 @@ def test_plan_a_entries_are_the_linear_part():
     p = team_plan(circ)
     assert p["nA"] < p["nJ"]  # the NMOS gate columns exist in J only
     assert p["chain"] == 0 and p["ovfptr"][-1] > 0 and p["ellW"] == 4  # the supply rail: wide elimination steps, a long row
+    assert p["nEarly"] >= 36  # every stage of the chain is an early step (nothing writes its pivot or its column entries)
+    circ = nl.load(CIRCUITS["ladder64"]())
+    assert team_plan(circ)["nEarly"] <= 3  # a ladder: every step updates the next pivot
 
 
 @pytest.mark.gpu
