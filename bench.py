@@ -8,8 +8,8 @@ reference would print (one .op result, one .dc sweep point, one accepted .tran s
 
 Headline (the JSON line's top level) = config C4 of SURVEY.md §8(d): the 64-node RC/RL ladder (n = 65), SIN drive,
 .TRAN with 1 ns maximum step, 65 536 Monte-Carlo instances per GPU.  The named span (5.4 us, ~10 k accepted steps per
-instance, 6.6e8 solve-points per GPU) takes ~15 s per pass, so one timed step runs every instance from t = 0 over 1/10
-of it (0.54 us, ~1060 accepted steps per instance, start-up .op and the h ramp-up included); `--full-span` times the whole span instead
+instance, 6.6e8 solve-points per GPU) takes ~12 s per pass, so one timed step runs every instance from t = 0 over 1/5
+of it (1.08 us, ~2070 accepted steps per instance, start-up .op and the h ramp-up included); `--full-span` times the whole span instead
 (the full-span numbers of the round are committed under profiles/).  `configs` holds the other named configs measured in
 the same run, each with its own roofline / cpu_baseline / e2e: C2 (.op, 65 536 instances per GPU), C3 (.dc, 1 M sweep
 points in total) and C5 (.tran, 256-node inverter chain, 16 384 instances in total, 4 ns of the 168 ns span per step).
@@ -71,7 +71,7 @@ def make_workload(name: str, scale: float, world: int, full_span: bool = False, 
                           f"sharded over the GPUs")
     if name == "c4":
         circ = nl.load(nl.ladder_netlist(64, "SIN( 0.0 1.0 10M )", stop="5.4u", step="1n"))
-        stop = tran_stop or (5.4e-6 if full_span else 5.4e-6 / 10.0)
+        stop = tran_stop or (5.4e-6 if full_span else 5.4e-6 / 5.0)
         span = "the full named span" if stop == 5.4e-6 else f"{stop:g}s = 1/{5.4e-6 / stop:g} of the named 5.4us span per step"
         return dict(name="c4", kind="tran", circ=circ, batch=max(1, int(65536 * scale)), stop=stop, step=1e-9, scaling="weak",
                     full_stop=5.4e-6,

@@ -478,7 +478,7 @@ def test_mid_size_kernels_agree_bitwise(which):
     assert v_sp.startswith("spw_n"), v_sp
     assert c_sp["redo"] == 0, c_sp
     if tran:
-        assert v_def.startswith("team" if which != "inverter130" else "spw"), v_def  # (n = 132: 27 KB per instance, too few warps)
+        assert v_def.startswith("team"), v_def
         for a, b in zip(o_sp, o_def):
             assert np.array_equal(a, b, equal_nan=True), v_def
         for lanes in (4, 8, 16, 32):
