@@ -128,6 +128,7 @@ struct ftsb_circuit {
     int team_state = 0;    // 0 = not tried, 1 = plan on the device, -1 = no usable plan
     int team_opt = 1;      // option "team": 1 (default) use them, 0 = the warp-per-instance kernels as before
     int team_g = 0;        // option "team_lanes": lanes per instance (0 = automatic)
+    int team_rows = 1;     // option "team_rows": 1 (default) linear circuits use the kernels with compile-time rows per lane when one fits
     int team_place = -1;   // option "team_place": 0 slot table and factors in global scratch, 3 in shared memory (-1 = automatic)
     int l2_persist = 1;    // option "l2_persist": keep the per-warp global scratch rows resident in L2 (access policy window)
     size_t l2_set_aside = 0, l2_window_max = 0;
@@ -801,7 +802,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     int place = 0;
     // lanes per instance: rows are dealt round-robin, so few lanes waste little; more teams per warp amortise the
     // list-walking code over more instances but need more shared memory per warp
-    int best_g = 0, best_occ = 0, best_wpb = 0;
+    int best_g = 0, best_occ = 0, best_wpb = 0, best_rows = 0;
     size_t best_smem = 0;
     TeamLayout best_lay{};
     for (int place_try : {c->team_place >= 0 ? (c->team_place & 7) : (linear ? 0 : 3), -1}) {
@@ -810,12 +811,21 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     for (int g : {8, 16, 32}) {
         if (c->team_g > 0) g = c->team_g;
         TeamKernelFn fn = (mo.n + g - 1) / g <= 32 ? team_kernel(g, place, ph.ellW) : nullptr; // rows per lane fit a 32-bit class mask
+        // linear circuit, rows per lane among the instantiated counts: registers instead of shared-memory round trips
+        int rows = 0;
+        if (linear && ph.chain && g == TEAM_CHUNK && (place & 2) == 0 && c->team_rows && (mo.n + g - 1) / g <= 32) {
+            TeamKernelFn fr = team_kernel_rows(g, place, ph.ellW, (mo.n + g - 1) / g);
+            if (fr) {
+                fn = fr;
+                rows = (mo.n + g - 1) / g;
+            }
+        }
         if (fn) {
             const int T = 32 / g;
             const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place);
             int w_best = 0, occ_best = 0;
             size_t smem_best = 0;
-            for (int wpb = TEAM_WARPS_MAX; wpb >= 1; --wpb) { // warps per block: whatever packs most warps onto an SM
+            for (int wpb = rows ? TEAM_WARPS_ROWS : TEAM_WARPS_MAX; wpb >= 1; --wpb) { // warps per block: whatever packs most warps onto an SM
                 const size_t smem = (size_t)2 * FTS_LOG1P_N * 8 + (size_t)wpb * lay.sm_doubles * T * 8;
                 int occ = 0;
                 if (smem <= c->smem_optin &&
@@ -833,6 +843,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
             // that (n = 258: 50 KB per instance) stays with the warp kernel and its global scratch rows
             if (w_best && (c->team_g > 0 || occ_best * w_best >= 8)) {
                 best_g = g;
+                best_rows = rows;
                 best_occ = occ_best;
                 best_wpb = w_best;
                 best_smem = smem_best;
@@ -844,7 +855,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     }
     if (!best_g) return 1;
     const int T = 32 / best_g;
-    tl.fn = team_kernel(best_g, place, ph.ellW);
+    tl.fn = best_rows ? team_kernel_rows(best_g, place, ph.ellW, best_rows) : team_kernel(best_g, place, ph.ellW);
     tl.g = best_g;
     tl.place = place;
     tl.wpb = best_wpb;
@@ -860,7 +871,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
         cudaGetLastError();
         return 1;
     }
-    c->variant = "team" + std::to_string(best_g) + "p" + std::to_string(place) + "_n" + std::to_string(mo.n) + "/A" + std::to_string(ph.nA) +
+    c->variant = "team" + std::to_string(best_g) + "p" + std::to_string(place) + (best_rows ? "r" + std::to_string(best_rows) : std::string()) + "_n" + std::to_string(mo.n) + "/A" + std::to_string(ph.nA) +
                  "/S" + std::to_string(ph.S) + (ph.chain ? "/chain" : "") + "/occ" + std::to_string(best_occ) + "x" + std::to_string(best_wpb);
     return 0;
 }
@@ -1184,6 +1195,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->team_opt = value ? 1 : 0;
     else if (!strcmp(name, "team_lanes"))
         c->team_g = (int)value;
+    else if (!strcmp(name, "team_rows"))
+        c->team_rows = value ? 1 : 0;
     else if (!strcmp(name, "team_place"))
         c->team_place = (int)value;
     else if (!strcmp(name, "hist_global"))

@@ -35,6 +35,19 @@ TeamKernelFn team_kernel(int g, int place, int ell_w)
         return nullptr;
     }
 }
+TeamKernelFn team_kernel_rows_w3a(int rows); // kern_team_rows3a.cu ...
+TeamKernelFn team_kernel_rows_w3b(int rows);
+TeamKernelFn team_kernel_rows_w4a(int rows);
+TeamKernelFn team_kernel_rows_w4b(int rows);
+// linear circuits with a chain plan, 8 lanes per instance, slot table and factors in the global scratch (place 0),
+// 3 <= rows per lane <= 12 (17 <= n <= 96)
+TeamKernelFn team_kernel_rows(int g, int place, int ell_w, int rows)
+{
+    if (g != 8 || place != 0 || rows < 3 || rows > 12) return nullptr;
+    if (ell_w == 3) return rows <= 7 ? team_kernel_rows_w3a(rows) : team_kernel_rows_w3b(rows);
+    if (ell_w == 4) return rows <= 7 ? team_kernel_rows_w4a(rows) : team_kernel_rows_w4b(rows);
+    return nullptr;
+}
 } // namespace ftsb
 
 // ---------------------------------------------------------------------------------------------------------

@@ -79,7 +79,8 @@ struct TeamArgs {
     long long flops_factor, flops_solve;
 };
 
-constexpr int TEAM_WARPS_MAX = 8; // warps per block (they share the ln_1p table); the launcher picks the count
+constexpr int TEAM_WARPS_MAX = 8;  // warps per block (they share the ln_1p table); the launcher picks the count
+constexpr int TEAM_WARPS_ROWS = 12; // the same for the kernels with compile-time rows per lane (RC > 0): three warps per scheduler leave 168 registers (four: 128)
 
 template <int G>
 struct TeamOps {
@@ -269,6 +270,7 @@ struct TeamOps {
     // rounded quotient (Markstein) as long as nothing overflows / underflows — checked on the exponents; everything
     // else (zero, tiny, huge, infinite, NaN operands) takes the division itself.  Bit-identical to y / d
     // (tests: test_team_exact_division_*), five instructions instead of ~30 on the critical path of the back substitution.
+    static __device__ __noinline__ double div_plain(double y, double d) { return y / d; }
     static __device__ __forceinline__ double div_known_rcp(double y, double d, double al)
     {
         const unsigned ey = ((unsigned)__double2hiint(y) >> 20) & 0x7ffu, ed = ((unsigned)__double2hiint(d) >> 20) & 0x7ffu;
@@ -277,7 +279,7 @@ struct TeamOps {
             const double r0 = fma(-d, q0, y);
             return fma(r0, al, q0);
         }
-        return y / d;
+        return div_plain(y, d); // (out of line: the streams inline this function several times)
     }
     // s / c for a small positive integer c (class sizes): same construction; s >= 0 is a square root, zero or normal
     static __device__ __forceinline__ double div_count(double s, double c, double rc)
@@ -288,6 +290,30 @@ struct TeamOps {
             return fma(r0, rc, q0);
         }
         return s / c; // inf, NaN
+    }
+
+    // The class norm s = sqrt(q) / count of a sum of squares q (node_vec_norm.rs:12-33) enters the convergence test only as
+    // `s < 0.001 * s + tol` (newtons_method.rs:79-89 with err_old == err, step_old == step: they are cloned at the end of the
+    // previous iteration, :62-63).  sqrt and the division are correctly rounded and monotone in q, and s -> fl(fl(0.001 s) + tol)
+    // is non-decreasing with slope << 1, so the test holds exactly for the q below one threshold: found here by bisection on
+    // the bit pattern with the very operations the generic loop uses.  count = 0 (an empty class: 0 / 0 = NaN, never
+    // converged) gives 0.0, which no q >= 0 is below.  tests/test_host_logic.py checks the monotonicity argument in numpy.
+    static __device__ double norm_threshold(double dn, double rn, double tol)
+    {
+        auto ok = [&](double q) {
+            const double s = div_count(sqrt(q), dn, rn);
+            return s < 0.001 * s + tol;
+        };
+        if (!ok(0.0)) return 0.0;
+        unsigned long long lo = 0ULL, hi = 0x7ff0000000000000ULL; // ok(lo), !ok(hi)
+        while (hi - lo > 1ULL) {
+            const unsigned long long mid = lo + ((hi - lo) >> 1);
+            if (ok(__longlong_as_double((long long)mid)))
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return __longlong_as_double((long long)hi);
     }
 
     // The substitutions as op streams (team_plan.h): lane 0 of the team walks the ops in order — a chain of dependent
@@ -540,9 +566,11 @@ struct TeamOps {
     }
 };
 
-// place: see team_layout
-template <int G, int PLACE, int W>
-__global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __grid_constant__ RunArgs a, const __grid_constant__ TeamArgs ta)
+// place: see team_layout.  RC > 0: LINEAR circuits whose rows per lane (n + G - 1) / G equal RC — the Newton loop keeps the
+// lane's rows of x and x_proposed in registers, addresses its rows at compile-time offsets, decides convergence on the sums
+// of squares (norm_threshold) and evaluates the residual only in the iterations whose step test passes (see the loop).
+template <int G, int PLACE, int W, int RC = 0>
+__global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MAX)) __maxnreg__(RC > 0 ? 168 : 128) k_team_tran(const __grid_constant__ RunArgs a, const __grid_constant__ TeamArgs ta)
 {
     using Ops = TeamOps<G>;
     constexpr int T = Ops::T;
@@ -570,8 +598,8 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
     const V sv{((PLACE & 2) ? sw : gw) + L.osv * T}, alpha{((PLACE & 2) ? sw : gw) + L.oalpha * T};
     const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T};
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const bool linear = M.n_nl == 0;
-    const bool chain = P.chain != 0 && G <= TEAM_CHUNK; // single-lane op streams (ladders); wider teams: lane-parallel lists
+    const bool linear = RC > 0 || M.n_nl == 0;                       // (RC > 0: guaranteed by the launcher, as is the chain plan)
+    const bool chain = RC > 0 || (P.chain != 0 && G <= TEAM_CHUNK); // single-lane op streams (ladders); wider teams: lane-parallel lists
     const int R = (n + G - 1) / G; // rows per lane: row i = j * G + l, j < R
     unsigned clsmask = 0;          // bit j: row j * G + l is a current row (NodeType::Current); R <= 32 (launcher)
     for (int j = 0; j < R && j < 32; ++j) {
@@ -581,6 +609,11 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
     auto is_cur = [&](int j, int) -> bool { return ((clsmask >> j) & 1u) != 0u; };
     const double dnv = (double)M.nv, dni = (double)M.ni, rnv = 1.0 / dnv, rni = 1.0 / dni;
     const bool has_ovf = P.nSlotA > W * (n + 1);
+    double thr_v = 0.0, thr_i = 0.0; // RC > 0: the convergence tests as thresholds on the class sums of squares
+    if constexpr (RC > 0) {
+        thr_v = Ops::norm_threshold(dnv, rnv, 1e-6);
+        thr_i = Ops::norm_threshold(dni, rni, 1e-9);
+    }
     // the zero row (index n of x, x_proposed, b; row n of A): written once, never touched by an instance
     if (l == 0) {
         x[n] = 0.0;
@@ -594,9 +627,9 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
     long long inst = -1, nrec = 0, stored = 0;
     int status = ST_OK;
     double t = 0.0, h = 1e-18, hA = -1.0, h_first = 1e-18, tr0 = 0.0, tr1 = 0.0, tr2 = 0.0;
-    unsigned long long ci[CN_LOCAL], cn[CN_LOCAL]; // the instance in flight / finished instances
+    unsigned long long ci[CN_LOCAL]; // the instance in flight (added to the global counters when it finishes)
 #pragma unroll
-    for (int i = 0; i < CN_LOCAL; ++i) ci[i] = cn[i] = 0;
+    for (int i = 0; i < CN_LOCAL; ++i) ci[i] = 0;
     const unsigned long long total = a.in_list ? *a.in_count : (unsigned long long)a.batch;
 
     for (;;) {
@@ -743,6 +776,119 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
                 __syncwarp();
             }
             // ------------------------------------------------------------ Newton (newtons_method.rs:19-71), all teams in rounds
+            if constexpr (RC > 0) {
+                // ---- linear circuit, RC rows per lane (row j * G + l, the last one clamped to the zero row).  The proposed solution
+                // does not move inside the call, so every unknown iterates on its own — x_i += damp(xp_i - x_i) — and the unknowns
+                // meet only in the norms: x and x_proposed stay in registers.  converged() (newtons_method.rs:79-89) is a
+                // conjunction of the step test and the residual test, each on the current iteration's own norms; the residual is
+                // therefore evaluated only in the iterations whose step test passes.  What the reference does with a residual
+                // that is not evaluated here is the `is_infinite` panic (:53-55): it cannot fire when every |a(r,c)|, |b_r|,
+                // |x_i| and |xp_i| of the call is below 1e70 (|x_k - xp| never grows under the damping, so every iterate stays
+                // below 3e70 and a sum of n < 65 536 squares of |f_r| < 2e145 is finite); an instance that fails this guard
+                // evaluates the residual in every iteration like the generic loop.
+                const int il = min((RC - 1) * G + l, n);
+                const int2 *ellc = reinterpret_cast<const int2 *>(P.ellcol);
+                constexpr bool XP_REG = RC <= 10; // x_proposed in registers too (otherwise one shared-memory load per row and iteration)
+                double xr[RC], xpr[XP_REG ? RC : 1];
+                bool big = false;
+#pragma unroll
+                for (int j = 0; j < RC; ++j) {
+                    const int i = j < RC - 1 ? j * G + l : il;
+                    xr[j] = x[i];
+                    const double xpj = xp[i];
+                    if (XP_REG) xpr[j] = xpj;
+                    big |= !(fabs(xr[j]) < 1e70) || !(fabs(xpj) < 1e70) || !(fabs(b[i]) < 1e70);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) big |= !(fabs(A[i * W + w]) < 1e70);
+                    if (has_ovf && i < n) {
+                        const int v0 = __ldg(&P.ovfptr[i]), v1 = __ldg(&P.ovfptr[i + 1]);
+                        for (int c = v0; c < v1; ++c) big |= !(fabs(A[W * (n + 1) + c]) < 1e70);
+                    }
+                }
+                const bool lazy = !Ops::any(it_on && big, tmask);
+                bool sok = false, eok = false;
+                int it = 0;
+                for (;;) {
+                    if (it_on && !(it < 100 && !(sok && eok))) {
+                        it_on = false;
+                        r_newton = it < 100 ? it : -ST_NOT_CONVERGED;
+                    }
+                    if (!__any_sync(0xffffffffu, it_on)) break;
+                    double qv = 0.0, qi = 0.0;
+                    if (it_on) { // damped step (newtons_method.rs:73-77); x = x_new (:57-59)
+                        constexpr int RB = 3; // rows in flight: their ln_1p chains interleave
+#pragma unroll
+                        for (int j0 = 0; j0 < RC; j0 += RB) {
+                            double tt_[RB];
+#pragma unroll
+                            for (int u = 0; u < RB; ++u)
+                                if (j0 + u < RC) {
+                                    const double d = (XP_REG ? xpr[j0 + u] : xp[j0 + u < RC - 1 ? (j0 + u) * G + l : il]) - xr[j0 + u];
+                                    tt_[u] = (1.3 / 16.0) * copysign(1.0, d) * fts_log1p_pos(16.0 * fabs(d), tab);
+                                }
+#pragma unroll
+                            for (int u = 0; u < RB; ++u)
+                                if (j0 + u < RC) {
+                                    xr[j0 + u] = xr[j0 + u] + tt_[u];
+                                    if (is_cur(j0 + u, 0))
+                                        qi += tt_[u] * tt_[u];
+                                    else
+                                        qv += tt_[u] * tt_[u];
+                                }
+                        }
+                    }
+                    Ops::sum2(qv, qi);
+                    sok = qv < thr_v && qi < thr_i;
+                    const bool need = it_on && (sok || !lazy);
+                    double fv = 0.0, fi = 0.0;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (need) {
+#pragma unroll
+                            for (int j = 0; j < RC; ++j) x[j < RC - 1 ? j * G + l : il] = xr[j];
+                        }
+                        __syncwarp();
+                        if (need) { // f = A x - b (mna.rs:25-29) and its class sums (node_vec_norm.rs:12-33)
+#pragma unroll
+                            for (int j = 0; j < RC; ++j) {
+                                const int row = j < RC - 1 ? j * G + l : il;
+                                const int2 cols = __ldg(ellc + row);
+                                double ax = 0.0;
+#pragma unroll
+                                for (int w = 0; w < W; ++w) { // the row's entries in column order, separate multiply and add
+                                    const int cw = w < 2 ? cols.x : cols.y;
+                                    const int col = (w & 1) ? (cw >> 16) & 0xffff : cw & 0xffff;
+                                    ax = ax + A[row * W + w] * x[col];
+                                }
+                                if (has_ovf && row < n) {
+                                    const int v0 = __ldg(&P.ovfptr[row]), v1 = __ldg(&P.ovfptr[row + 1]);
+                                    for (int c = v0; c < v1; ++c) ax = ax + A[W * (n + 1) + c] * x[__ldg(&P.ovfcol[c])]; // long rows
+                                }
+                                const double f = ax + 0.0 - b[row];
+                                if (is_cur(j, 0))
+                                    fi += f * f;
+                                else
+                                    fv += f * f;
+                            }
+                        }
+                        Ops::sum2(fv, fi);
+                        __syncwarp();
+                    }
+                    if (it_on) {
+                        eok = need && fv < thr_v && fi < thr_i;
+                        ++it;
+                        ci[CN_NEWTON]++;
+                        if (need && (fv == INF || fi == INF)) { // the reference panics: reproduced from scratch by the warp kernel
+                            redo = true;
+                            it_on = false;
+                        }
+                    }
+                }
+                if (act) { // the last iterate (x is not restored after a rejected attempt either, quirk Q11)
+#pragma unroll
+                    for (int j = 0; j < RC; ++j) x[j < RC - 1 ? j * G + l : il] = xr[j];
+                }
+                __syncwarp();
+            } else {
             int flags = Ops::eval_nl(M, x, val, l, it_on);
             if (it_on && (flags >> 20)) {
                 redo = true; // NMOS_UNREACHABLE: the warp kernel reproduces the reference's panic from scratch
@@ -881,6 +1027,7 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
                 }
                 __syncwarp();
             }
+            }
             // ------------------------------------------------------------ accept / reject (transient.rs:48-91)
             bool accepted = false;
             double next_h = h;
@@ -1001,23 +1148,20 @@ __global__ void __launch_bounds__(32 * TEAM_WARPS_MAX, 2) k_team_tran(const __gr
                     if (l == 0) {
                         a.n_rec[inst] = nrec;
                         a.status[inst] = status;
-                    }
 #pragma unroll
-                    for (int i = 0; i < CN_LOCAL; ++i) cn[i] += ci[i];
+                        for (int i = 0; i < CN_LOCAL; ++i)
+                            if (ci[i]) atomicAdd(&a.counters[i], ci[i]);
+                    }
                 }
                 have = false;
             }
             __syncwarp();
         }
     }
-    if (l == 0) {
-#pragma unroll
-        for (int i = 0; i < CN_LOCAL; ++i)
-            if (cn[i]) atomicAdd(&a.counters[i], cn[i]);
-    }
 }
 
 typedef void (*TeamKernelFn)(const RunArgs, const TeamArgs);
-TeamKernelFn team_kernel(int g, int place, int ell_w); // kern_team.cu
+TeamKernelFn team_kernel(int g, int place, int ell_w);          // kern_team.cu
+TeamKernelFn team_kernel_rows(int g, int place, int ell_w, int rows); // kern_team_rows*.cu: linear circuits, rows per lane at compile time
 
 } // namespace ftsb

@@ -481,6 +481,14 @@ def test_mid_size_kernels_agree_bitwise(which):
         assert v_def.startswith("team"), v_def
         for a, b in zip(o_sp, o_def):
             assert np.array_equal(a, b, equal_nan=True), v_def
+        if which.startswith("ladder"):  # linear: the default is the kernel with compile-time rows per lane ("r<rows>")
+            rows = (circ.n_run + 7) // 8
+            assert v_def.startswith(f"team8p0r{rows}_"), v_def
+            v_gen, c_gen, o_gen = _run_mid(circ, vals, fns, {"team_rows": 0})
+            assert v_gen.startswith("team8p0_"), v_gen
+            assert c_gen == c_def, (c_gen, c_def)
+            for a, b in zip(o_gen, o_def):
+                assert np.array_equal(a, b, equal_nan=True), v_def
         for lanes in (4, 8, 16, 32):
             for place in (0, 1, 3, 6):
                 v_t, c_t, o_t = _run_mid(circ, vals, fns, {"team_lanes": lanes, "team_place": place})
@@ -503,6 +511,30 @@ def test_mid_size_kernels_agree_bitwise(which):
     for a, b, c in zip(o_sp, o_w, o_g):
         assert np.array_equal(a, b, equal_nan=True)
         assert np.array_equal(a, c, equal_nan=True)
+
+
+@pytest.mark.parametrize("scale", [1e30, 1e72, 1e160, float("inf")])
+def test_team_rows_kernel_lazy_residual_guard(scale):
+    """The compile-time-rows kernel skips the residual while the step test fails only when no residual of the call can
+    overflow (all magnitudes below 1e70).  Instances driven with huge sources must take the every-iteration path and still
+    equal the generic per-team kernel and the warp kernel bit for bit — including the reference's `is_infinite` panic
+    (status DIVERGED) and NaN runs that end as NOT_CONVERGED."""
+    circ = _mid_circuit("ladder24")
+    B = 12
+    vals, fns = nl.monte_carlo(circ, B)
+    fns = fns.copy()
+    src = [i for i in range(circ.n_elems) if circ.fn_kind[i] != 0]
+    assert src
+    for inst in range(0, B, 2):  # PULSE(v1 v2 ...): the start-up .op sees v1, the pulse then drives every other instance to v2 = scale
+        fns[inst, src[0], 1] = scale
+    v_def, c_def, o_def = _run_mid(circ, vals, fns, {})
+    v_gen, c_gen, o_gen = _run_mid(circ, vals, fns, {"team_rows": 0})
+    v_sp, c_sp, o_sp = _run_mid(circ, vals, fns, {"team": 0})
+    assert v_def.startswith("team8p0r4_") and v_gen.startswith("team8p0_") and v_sp.startswith("spw_n"), (v_def, v_gen, v_sp)
+    for a, b, c in zip(o_def, o_gen, o_sp):
+        assert np.array_equal(a, b, equal_nan=True)
+        assert np.array_equal(a, c, equal_nan=True)
+    assert (o_def[0][1::2] == 0).all()  # the untouched instances run to the end
 
 
 @pytest.mark.parametrize("which", ["ladder24", "inverter40", "ladder30_op"])

@@ -163,3 +163,33 @@ def test_synthetic_configs_shapes():
     assert c5.n_run == 258 and sum(1 for e in c5.elems if e.kind == nl.M) == 254
     c2 = nl.load(nl.PROJ1_NL)
     assert c2.n_start == 14 and sum(1 for e in c2.elems if e.kind in (nl.D, nl.Q)) == 2
+
+
+@pytest.mark.parametrize("count", [1, 2, 3, 7, 33, 64, 65, 129, 1000])
+@pytest.mark.parametrize("tol", [1e-6, 1e-9])
+def test_norm_convergence_test_is_a_threshold_on_the_sum_of_squares(count, tol):
+    """solver_team.cuh (compile-time-rows kernels) replaces `s < 0.001 * s + tol`, s = sqrt(q) / count, by `q < threshold`
+    with the threshold found by bisection on the bit pattern (TeamOps::norm_threshold).  That is exact iff the test is
+    monotone in q: checked here with IEEE double arithmetic (numpy: correctly rounded sqrt / divide, no contraction) on
+    40 000 neighbouring bit patterns around the threshold and on 200 000 random magnitudes."""
+    def ok(q):
+        s = np.sqrt(q) / np.float64(count)
+        return s < np.float64(0.001) * s + np.float64(tol)
+
+    lo, hi = 0, 0x7FF0000000000000
+    assert ok(np.float64(0.0)) and not ok(np.float64(np.inf))
+    while hi - lo > 1:
+        mid = lo + (hi - lo) // 2
+        if ok(np.array([mid], dtype=np.uint64).view(np.float64)[0]):
+            lo = mid
+        else:
+            hi = mid
+    thr = np.array([hi], dtype=np.uint64).view(np.float64)[0]
+    near = (np.arange(-20000, 20000, dtype=np.int64) + hi).astype(np.uint64).view(np.float64)
+    assert np.array_equal(ok(near), near < thr)
+    rng = np.random.default_rng(count)
+    q = np.exp(rng.uniform(np.log(thr) - 40.0, np.log(thr) + 40.0, 200000))
+    q = np.concatenate([q, thr * (1.0 + rng.uniform(-1e-9, 1e-9, 100000)), [0.0, np.inf]])
+    assert np.array_equal(ok(q), q < thr)
+    with np.errstate(invalid="ignore"):
+        assert not ok(np.float64(np.nan)) and not (np.float64(np.nan) < thr)
