@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
     bool have = false, exhausted = false, new_step = true;
     long long inst = -1, nrec = 0, stored = 0;
     int status = ST_OK;
-    double t = 0.0, h = 1e-18, hA = -1.0, h_first = 1e-18, tr0 = 0.0, tr1 = 0.0, tr2 = 0.0;
+    double t = 0.0, h = 1e-18, hA = -1.0, hV = -1.0, h_first = 1e-18, tr0 = 0.0, tr1 = 0.0, tr2 = 0.0;
     unsigned long long ci[CN_LOCAL]; // the instance in flight (added to the global counters when it finishes)
 #pragma unroll
     for (int i = 0; i < CN_LOCAL; ++i) ci[i] = 0;
@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                     t = 0.0;
                     h = 1e-18;
                     hA = -1.0;
+                    hV = -1.0;
                     tr0 = tr1 = tr2 = 0.0;
                     nrec = stored = 0;
                     new_step = true;
@@ -710,17 +711,18 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                 for (int i = l; i < DP.n_dyn; i += G) {
                     const int *dd = &DP.dyn[6 * i];
                     const int s = __ldg(&dd[1]), kind = __ldg(&dd[2]);
-                    const double u = state[2 * i], ic = state[2 * i + 1], pv = dynv[i];
-                    if (kind == K_C) {
-                        const double g = 2.0 * pv / h_first;
+                    const double u = state[2 * i], ic = state[2 * i + 1];
+                    double g; // kept in the slot table while h does not change (hV): same expression, same operands, same bits
+                    if (h_first == hV)
+                        g = val[s];
+                    else {
+                        const double pv = dynv[i];
+                        g = kind == K_C ? 2.0 * pv / h_first : h_first / (2.0 * pv);
                         val[s] = g;
-                        val[s + 1] = -(ic + g * u);
-                    } else {
-                        const double g = h_first / (2.0 * pv);
-                        val[s] = g;
-                        val[s + 1] = ic + g * u;
                     }
+                    val[s + 1] = kind == K_C ? -(ic + g * u) : ic + g * u;
                 }
+                hV = h_first;
             }
             const double te = t + h;
             if (act) { // time-varying sources at t + h (transient.rs:36-42); I sources drift (quirk Q9)
@@ -752,10 +754,45 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                 __syncwarp();
             }
             if (act) { // b of this attempt (sources do not change inside a Newton call)
-                for (int i = l; i < n; i += G) {
-                    const double bi = Ops::gsum(M.b_all, i, val, 0.0);
-                    b[i] = bi;
-                    if (linear) y[i] = bi;
+                if constexpr (RC > 0) { // EBR rows per batch: their index and slot-table loads overlap (same sums, same order)
+                    constexpr int EBR = 3;
+                    for (int i0 = l; i0 < n; i0 += EBR * G) {
+                        int c0[EBR], len[EBR], maxlen = 0;
+                        double acc[EBR];
+#pragma unroll
+                        for (int e = 0; e < EBR; ++e) {
+                            const int i = i0 + e * G;
+                            c0[e] = i < n ? __ldg(&M.b_all.ptr[i]) : 0;
+                            len[e] = i < n ? __ldg(&M.b_all.ptr[i + 1]) - c0[e] : 0;
+                            maxlen = max(maxlen, len[e]);
+                            acc[e] = 0.0;
+                        }
+                        for (int tt = 0; tt < maxlen; ++tt) {
+                            unsigned wd[EBR];
+#pragma unroll
+                            for (int e = 0; e < EBR; ++e) wd[e] = tt < len[e] ? (unsigned)__ldg(&M.b_all.con[c0[e] + tt]) : 0u;
+                            double v[EBR];
+#pragma unroll
+                            for (int e = 0; e < EBR; ++e) v[e] = tt < len[e] ? val[wd[e] & ~CON_NEG] : 0.0;
+#pragma unroll
+                            for (int e = 0; e < EBR; ++e)
+                                if (tt < len[e]) acc[e] += (wd[e] & CON_NEG) ? -v[e] : v[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < EBR; ++e) {
+                            const int i = i0 + e * G;
+                            if (i < n) {
+                                b[i] = acc[e];
+                                y[i] = acc[e];
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = l; i < n; i += G) {
+                        const double bi = Ops::gsum(M.b_all, i, val, 0.0);
+                        b[i] = bi;
+                        if (linear) y[i] = bi;
+                    }
                 }
             }
             __syncwarp();
@@ -1043,10 +1080,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                     const double a01 = 1.0 / (tr1 - tr0), a12 = 1.0 / (tr2 - tr1), a23 = 1.0 / (te - tr2);
                     const double a02 = 1.0 / (tr2 - tr0), a13 = 1.0 / (te - tr1), a03 = 1.0 / (te - tr0);
                     const int o0 = (int)(nrec % 3), o1 = (int)((nrec + 1) % 3), o2 = (int)((nrec + 2) % 3);
-#pragma unroll 3
-                    for (int j = 0; j < R; ++j) {
-                        const int i = j * G + l;
-                        if (i >= n) break;
+                    auto plte_row = [&](int j, int i) {
                         const double x0 = ring[o0 * n + i], x1 = ring[o1 * n + i], x2 = ring[o2 * n + i];
                         const double x3 = x[i];
                         const double d01 = a01 * (x1 - x0), d12 = a12 * (x2 - x1), d23 = a23 * (x3 - x2);
@@ -1059,6 +1093,20 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                         } else {
                             pv += pl * pl;
                             xv += x3 * x3;
+                        }
+                    };
+                    if constexpr (RC > 0) { // all rows unrolled: the ring loads (L2) of the lane's rows are in flight together
+#pragma unroll
+                        for (int j = 0; j < RC; ++j) {
+                            const int i = j * G + l;
+                            if (j < RC - 1 || i < n) plte_row(j, i);
+                        }
+                    } else {
+#pragma unroll 3
+                        for (int j = 0; j < R; ++j) {
+                            const int i = j * G + l;
+                            if (i >= n) break;
+                            plte_row(j, i);
                         }
                     }
                 }
