@@ -128,6 +128,7 @@ struct ftsb_circuit {
     int team_state = 0;    // 0 = not tried, 1 = plan on the device, -1 = no usable plan
     int team_opt = 1;      // option "team": 1 (default) use them, 0 = the warp-per-instance kernels as before
     int team_g = 0;        // option "team_lanes": lanes per instance (0 = automatic)
+    int team_levels = 1;   // option "team_levels": 1 (default) level-scheduled elimination / substitutions for factors in shared memory, 0 = one lane walks them
     int team_rows = 1;     // option "team_rows": 1 (default) linear circuits use the kernels with compile-time rows per lane when one fits
     int team_place = -1;   // option "team_place": 0 slot table and factors in global scratch, 3 in shared memory (-1 = automatic)
     int l2_persist = 1;    // option "l2_persist": keep the per-warp global scratch rows resident in L2 (access policy window)
@@ -864,6 +865,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     tl.grid = (int)std::max(1LL, std::min((batch + per_block - 1) / per_block, (long long)best_occ * c->sm_count));
     tl.scratch_bytes = (size_t)tl.grid * best_wpb * best_lay.gl_doubles * T * 8;
     tl.ta.plan = ph.view((const int *)c->team_buf.p);
+    tl.ta.plan.levels = c->team_levels;
     tl.ta.lay = best_lay;
     tl.ta.flops_factor = ph.flops_factor;
     tl.ta.flops_solve = ph.flops_solve;
@@ -1195,6 +1197,8 @@ int ftsb_set_option(ftsb_circuit *c, const char *name, int64_t value)
         c->team_opt = value ? 1 : 0;
     else if (!strcmp(name, "team_lanes"))
         c->team_g = (int)value;
+    else if (!strcmp(name, "team_levels"))
+        c->team_levels = value ? 1 : 0;
     else if (!strcmp(name, "team_rows"))
         c->team_rows = value ? 1 : 0;
     else if (!strcmp(name, "team_place"))
@@ -1968,6 +1972,8 @@ extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int
     std::copy(m2, m2 + 16, meta + 25); // meta[25..40]
     const int m3[] = {ph.nEarly, ph.nXop, ph.nDFop, ph.nDBop, ph.o_early, ph.o_xop, ph.o_dfop, ph.o_dbop};
     std::copy(m3, m3 + 8, meta + 41); // meta[41..48]: the direct streams
+    const int m4[] = {ph.nXlev, ph.nFlev, ph.nBlev, ph.o_xlptr, ph.o_xlop, ph.o_flptr, ph.o_flop, ph.o_blptr, ph.o_blop};
+    std::copy(m4, m4 + 9, meta + 49); // meta[49..57]: the level schedules
     for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
     std::copy(pv.begin(), pv.end(), piv);
     return 0;

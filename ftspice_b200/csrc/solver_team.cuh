@@ -549,6 +549,85 @@ struct TeamOps {
         return !any(bad, tmask);
     }
 
+    // ---- level schedules (team_plan.h): the ops of a level on the lanes of the team, a warp barrier between levels ----
+    static __device__ bool factor_levels(const TeamPlan &P, V sv, V alpha, int l, bool on, unsigned tmask)
+    {
+        bool bad = false;
+        const int2 *ops = reinterpret_cast<const int2 *>(P.xlop);
+        const int nlev = P.nXlev;
+        int o0 = __ldg(&P.xlptr[0]), o1 = __ldg(&P.xlptr[1]);
+        for (int L = 0; L < nlev; ++L) {
+            const int o2 = L + 2 <= nlev ? __ldg(&P.xlptr[L + 2]) : o1; // (one level ahead: off the critical path)
+            for (int o = o0 + l; o < o1; o += G) {
+                const int2 w = __ldg(ops + o);
+                if (on) {
+                    if (w.y < 0)
+                        bad |= step_head(P, sv, alpha, w.x);
+                    else {
+                        const double m = sv[w.y];
+                        if (m != 0.0) { // a - 0 * p == a
+                            const int d = w.x & 0xffff, s_ = (w.x >> 16) & 0xffff;
+                            sv[d] = sv[d] - m * sv[s_]; // (:35-39)
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            o0 = o1;
+            o1 = o2;
+        }
+        return any(on && bad, tmask);
+    }
+    static __device__ void forward_levels(const TeamPlan &P, V sv, V y, int l, bool on)
+    {
+        const int2 *ops = reinterpret_cast<const int2 *>(P.flop);
+        const int nlev = P.nFlev;
+        int o0 = __ldg(&P.flptr[0]), o1 = __ldg(&P.flptr[1]);
+        for (int L = 0; L < nlev; ++L) {
+            const int o2 = L + 2 <= nlev ? __ldg(&P.flptr[L + 2]) : o1;
+            for (int o = o0 + l; o < o1; o += G) {
+                const int2 w = __ldg(ops + o);
+                if (on) {
+                    const double m = sv[w.y];
+                    if (m != 0.0) {
+                        const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
+                        y[r] = y[r] - m * y[pk]; // (:40)
+                    }
+                }
+            }
+            __syncwarp();
+            o0 = o1;
+            o1 = o2;
+        }
+    }
+    static __device__ bool backward_levels(const TeamPlan &P, V sv, V alpha, V y, V xp, int l, bool on, unsigned tmask)
+    {
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        bool bad = false;
+        const int2 *ops = reinterpret_cast<const int2 *>(P.blop);
+        const int nlev = P.nBlev;
+        int o0 = __ldg(&P.blptr[0]), o1 = __ldg(&P.blptr[1]);
+        for (int L = 0; L < nlev; ++L) {
+            const int o2 = L + 2 <= nlev ? __ldg(&P.blptr[L + 2]) : o1;
+            for (int o = o0 + l; o < o1; o += G) {
+                const int2 w = __ldg(ops + o);
+                if (on) {
+                    const int row = w.x & 0xffff, i = (w.x >> 16) & 0xffff;
+                    if (w.y < 0) { // x_i = y[pivot row] / pivot (gauss_lu.rs:47)
+                        const double xi = div_known_rcp(y[row], sv[w.y & 0xffff], alpha[i]);
+                        xp[i] = xi;
+                        bad |= !(fabs(xi) < INF);
+                    } else // y[r] -= x_i * u(r, i) (:49-52)
+                        y[row] = y[row] - xp[i] * sv[w.y];
+                }
+            }
+            __syncwarp();
+            o0 = o1;
+            o1 = o2;
+        }
+        return !any(on && bad, tmask);
+    }
+
     // nonlinear devices at x -> slot values; returns team-wide (#non-finite currents) | panic << 20
     static __device__ __forceinline__ int eval_nl(const ModeProg &M, V x, V val, int l, bool on)
     {
@@ -946,9 +1025,15 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                     Ops::assemble_sv(P, val, sv, l, it_on);
                     __syncwarp();
                     if constexpr ((PLACE & 2) != 0) { // factors in shared memory: early steps in parallel, then one op stream
-                        if (Ops::factor_direct(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
-                        Ops::forward_direct(P, sv, y, l, it_on);
-                        if (!Ops::backward_direct(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
+                        if (P.levels) { // level schedules: all lanes of the team, a barrier per level
+                            if (Ops::factor_levels(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                            Ops::forward_levels(P, sv, y, l, it_on);
+                            if (!Ops::backward_levels(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
+                        } else { // early steps in parallel, then one lane walks the rest
+                            if (Ops::factor_direct(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                            Ops::forward_direct(P, sv, y, l, it_on);
+                            if (!Ops::backward_direct(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
+                        }
                     } else {
                         if (Ops::factor(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
                         if (chain) {

@@ -54,8 +54,51 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.xop = b + o_xop;
     p.dfop = b + o_dfop;
     p.dbop = b + o_dbop;
+    p.levels = 1;
+    p.nXlev = nXlev;
+    p.nFlev = nFlev;
+    p.nBlev = nBlev;
+    p.xlptr = b + o_xlptr;
+    p.xlop = b + o_xlop;
+    p.flptr = b + o_flptr;
+    p.flop = b + o_flop;
+    p.blptr = b + o_blptr;
+    p.blop = b + o_blop;
     return p;
 }
+
+namespace {
+// level schedule of an op list (team_plan.h): locations are small integers; reads / writes per op
+struct LevOp {
+    int w0, w1;
+    std::vector<int> reads, writes;
+};
+void levelize(const std::vector<LevOp> &ops, int nloc, std::vector<int> &lptr, std::vector<int> &words)
+{
+    std::vector<int> ready(nloc, 0), lastread(nloc, 0), lev(ops.size(), 0);
+    int nlev = 0;
+    for (size_t o = 0; o < ops.size(); ++o) {
+        int L = 0;
+        for (int r : ops[o].reads) L = std::max(L, ready[r]);
+        for (int w : ops[o].writes) L = std::max(L, std::max(ready[w], lastread[w]));
+        L += 1;
+        for (int r : ops[o].reads) lastread[r] = std::max(lastread[r], L);
+        for (int w : ops[o].writes) ready[w] = L;
+        lev[o] = L;
+        nlev = std::max(nlev, L);
+    }
+    lptr.assign(nlev + 1, 0);
+    for (size_t o = 0; o < ops.size(); ++o) lptr[lev[o]]++;
+    for (int L = 1; L <= nlev; ++L) lptr[L] += lptr[L - 1];
+    std::vector<int> cur(lptr.begin(), lptr.end() - 1); // lptr[L - 1] = first op of level L (1-based levels)
+    words.assign(2 * ops.size(), 0);
+    for (size_t o = 0; o < ops.size(); ++o) { // stable: the original order inside a level
+        const int at = cur[lev[o] - 1]++;
+        words[2 * at] = ops[o].w0;
+        words[2 * at + 1] = ops[o].w1;
+    }
+}
+} // namespace
 
 bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivseq, TeamPlanHost &out)
 {
@@ -283,6 +326,69 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
             out.o_xop = push2(xop);
             out.o_dfop = push2(dfop);
             out.o_dbop = push2(dbop);
+            // ---- level schedules (locations: factor entry e -> e, reciprocal k -> S + k, y[r] -> r, x[i] -> n + i) ----
+            std::vector<LevOp> ops;
+            std::vector<int> lptr, words;
+            for (int k = 0; k < n; ++k) {
+                LevOp hd;
+                hd.w0 = k;
+                hd.w1 = (int)0x80000000u;
+                hd.reads.push_back(pive[k]);
+                for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) {
+                    hd.reads.push_back(tgt[tt] & 0xffff);
+                    hd.writes.push_back(tgt[tt] & 0xffff);
+                }
+                hd.writes.push_back(S + k);
+                ops.push_back(hd);
+                for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt)
+                    for (int u = uptr[tt]; u < uptr[tt + 1]; ++u) {
+                        LevOp up;
+                        up.w0 = updds[u];
+                        up.w1 = updm[u];
+                        up.reads = {updm[u], (updds[u] >> 16) & 0xffff, updds[u] & 0xffff};
+                        up.writes = {updds[u] & 0xffff};
+                        ops.push_back(up);
+                    }
+            }
+            levelize(ops, S + n, lptr, words);
+            out.nXlev = (int)lptr.size() - 1;
+            out.o_xlptr = push2(lptr);
+            out.o_xlop = push2(words);
+            ops.clear();
+            for (int k = 0; k < n; ++k)
+                for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) {
+                    LevOp f;
+                    f.w0 = tgtr[tt] | (pivrow[k] << 16);
+                    f.w1 = tgt[tt] & 0xffff;
+                    f.reads = {tgtr[tt], pivrow[k]};
+                    f.writes = {tgtr[tt]};
+                    ops.push_back(f);
+                }
+            levelize(ops, n, lptr, words);
+            out.nFlev = (int)lptr.size() - 1;
+            out.o_flptr = push2(lptr);
+            out.o_flop = push2(words);
+            ops.clear();
+            for (int i = n - 1; i >= 0; --i) {
+                LevOp dv;
+                dv.w0 = pivrow[i] | (i << 16);
+                dv.w1 = (int)(0x80000000u | (unsigned)pive[i]);
+                dv.reads = {pivrow[i]};
+                dv.writes = {n + i};
+                ops.push_back(dv);
+                for (int bb = bptr[i]; bb < bptr[i + 1]; ++bb) {
+                    LevOp up;
+                    up.w0 = bwdr[bb] | (i << 16);
+                    up.w1 = bwde[bb];
+                    up.reads = {n + i, bwdr[bb]};
+                    up.writes = {bwdr[bb]};
+                    ops.push_back(up);
+                }
+            }
+            levelize(ops, 2 * n, lptr, words);
+            out.nBlev = (int)lptr.size() - 1;
+            out.o_blptr = push2(lptr);
+            out.o_blop = push2(words);
         }
         out.o_ellcol = push2(ellcol);
         out.o_ovfptr = push2(ovfptr);

@@ -70,6 +70,20 @@ struct TeamPlan {
     const int *xop;         // [nXop][2]
     const int *dfop;        // [nDFop][2]
     const int *dbop;        // [nDBop][2]
+    // ---- level schedules of the same three op sets (factors in shared memory): the ops are sorted into LEVELS such that an
+    //      op's operands are produced in earlier levels and nothing it overwrites is read later than its own level by another
+    //      op (read-after-write, write-after-write and write-after-read on the entries of the factors / y / x); the ops of a
+    //      level are dealt to the lanes of the team, a warp barrier separates levels.  Every value sees the same operations in
+    //      the same order as in the sequential streams, so the results are the same bits.  An inverter chain: 765 elimination
+    //      ops in 256 levels (all 257 early heads at once, then the rail recurrence), forward 509 ops in 256 levels, backward
+    //      512 ops in THREE levels (x_rail, all updates, all divides) instead of one lane walking 1 786 dependent ops.
+    //      xlop: as xop.  flop: as dfop.  blop: divide as dbop; update: word0 = row r | column i << 16 (x_i is read from
+    //      x_proposed), word1 = entry of U.
+    int levels;             // 1: use them (option team_levels)
+    int nXlev, nFlev, nBlev;
+    const int *xlptr, *xlop; // [nXlev + 1], [nXop][2] sorted by level
+    const int *flptr, *flop;
+    const int *blptr, *blop;
 };
 
 constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
@@ -83,6 +97,7 @@ struct TeamPlanHost {
     int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,
         o_bchunk = 0;
     int nEarly = 0, nXop = 0, nDFop = 0, nDBop = 0, o_early = 0, o_xop = 0, o_dfop = 0, o_dbop = 0;
+    int nXlev = 0, nFlev = 0, nBlev = 0, o_xlptr = 0, o_xlop = 0, o_flptr = 0, o_flop = 0, o_blptr = 0, o_blop = 0;
     long long flops_factor = 0, flops_solve = 0; // floating-point operations of one factorisation / one pair of substitutions
     TeamPlan view(const int *base) const;
 };

@@ -67,6 +67,11 @@ def team_plan(circ, an=2):
         p[k] = int(v)
     for k, o, ln in zip(["early", "xop", "dfop", "dbop"], meta[45:49], [p["nEarly"], 2 * p["nXop"], 2 * p["nDFop"], 2 * p["nDBop"]]):
         p[k] = ibuf[int(o):int(o) + ln].copy()
+    for k, v in zip(["nXlev", "nFlev", "nBlev"], meta[49:52]):
+        p[k] = int(v)
+    for k, o, ln in zip(["xlptr", "xlop", "flptr", "flop", "blptr", "blop"], meta[52:58],
+                        [p["nXlev"] + 1, 2 * (p["n"] + p["nU"]), p["nFlev"] + 1, 2 * p["nDFop"], p["nBlev"] + 1, 2 * p["nDBop"]]):
+        p[k] = ibuf[int(o):int(o) + ln].copy()
     p["jdst"] = jdst[:p["nJ"]].copy()
     p["piv"] = piv[:p["n"]].copy()
     return p
@@ -151,6 +156,66 @@ def run_direct(p, vals, rhs):
             x[i] = xi
         else:
             y[w0] = y[w0] - xi * sv[w1]
+    return x
+
+
+def run_levels(p, vals, rhs, rng):
+    """factor_levels / forward_levels / backward_levels of solver_team.cuh: the ops of a level run on different lanes at the
+    same time — here in a RANDOM order inside the level, reading the state as it stood when the level began and writing at
+    its end (what lanes between two warp barriers may observe at worst): the result must not depend on it."""
+    n, S = p["n"], p["S"]
+    sv = np.zeros(S)
+    sv[:p["nJ"]] = vals
+    alpha = np.zeros(n)
+    y = rhs.copy()
+    x = np.full(n, np.nan)
+
+    def walk(lptr, ops, nops, exec_op, arrays):
+        assert lptr[0] == 0 and lptr[-1] == nops and np.all(np.diff(lptr) > 0)
+        for L in range(len(lptr) - 1):
+            snap = [a.copy() for a in arrays]  # operands as they stood at the barrier
+            writes = {}
+            for o in rng.permutation(np.arange(lptr[L], lptr[L + 1])):
+                for key, v in exec_op(int(ops[2 * o]), int(ops[2 * o + 1]), *snap):
+                    assert key not in writes, "two ops of a level write the same location"
+                    writes[key] = v
+            for (ai, idx), v in writes.items():
+                arrays[ai][idx] = v
+
+    def x_op(w0, w1, sv_, alpha_):
+        out = []
+        if w1 < 0:
+            k = w0
+            al = np.float64(1.0) / sv_[p["pive"][k]]
+            out.append(((1, k), al))
+            for tt in range(p["tptr"][k], p["tptr"][k + 1]):
+                e = p["tgt"][tt] & 0xffff
+                out.append(((0, e), al * sv_[e]))
+        else:
+            m = sv_[w1]
+            if m != 0.0:
+                d, s_ = w0 & 0xffff, (w0 >> 16) & 0xffff
+                out.append(((0, d), sv_[d] - m * sv_[s_]))
+        return out
+
+    walk(p["xlptr"], p["xlop"], p["n"] + p["nU"], x_op, [sv, alpha])  # every head + every update
+
+    def f_op(w0, w1, y_):
+        m = sv[w1]
+        if m != 0.0:
+            r, pk = w0 & 0xffff, (w0 >> 16) & 0xffff
+            return [((0, r), y_[r] - m * y_[pk])]
+        return []
+
+    walk(p["flptr"], p["flop"], p["nDFop"], f_op, [y])
+
+    def b_op(w0, w1, y_, x_):
+        row, i = w0 & 0xffff, (w0 >> 16) & 0xffff
+        if w1 < 0:
+            return [((1, i), y_[row] / sv[w1 & 0xffff])]
+        return [((0, row), y_[row] - x_[i] * sv[w1])]
+
+    walk(p["blptr"], p["blop"], p["nDBop"], b_op, [y, x])
     return x
 
 
@@ -240,6 +305,7 @@ def test_plan_equals_dense_elimination_bitwise(which):
         assert np.array_equal(x_plan, x_dense), (which, trial, np.abs(x_plan - x_dense).max())
         assert np.array_equal(run_plan(p, vals, rhs, streams=True), x_dense), (which, trial, "op streams")
         assert np.array_equal(run_direct(p, vals, rhs), x_dense), (which, trial, "direct streams")
+        assert np.array_equal(run_levels(p, vals, rhs, rng), x_dense), (which, trial, "level schedules")
         assert np.abs(a @ x_plan - rhs).max() < 1e-6 * max(1.0, np.abs(x_plan).max())
 
 
