@@ -823,7 +823,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
         }
         if (fn) {
             const int T = 32 / g;
-            const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place);
+            const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place, linear ? 0 : ph.nJ);
             int w_best = 0, occ_best = 0;
             size_t smem_best = 0;
             for (int wpb = rows ? TEAM_WARPS_ROWS : TEAM_WARPS_MAX; wpb >= 1; --wpb) { // warps per block: whatever packs most warps onto an SM
@@ -1974,6 +1974,7 @@ extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int
     std::copy(m3, m3 + 8, meta + 41); // meta[41..48]: the direct streams
     const int m4[] = {ph.nXlev, ph.nFlev, ph.nBlev, ph.o_xlptr, ph.o_xlop, ph.o_flptr, ph.o_flop, ph.o_blptr, ph.o_blop};
     std::copy(m4, m4 + 9, meta + 49); // meta[49..57]: the level schedules
+    meta[58] = ph.o_spre;
     for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
     std::copy(pv.begin(), pv.end(), piv);
     return 0;

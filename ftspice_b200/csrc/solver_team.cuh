@@ -34,13 +34,13 @@ namespace ftsb {
 struct TeamLayout {
     int ox, oxp, ob, oy, oA, oprev, ostg; // shared (stg: two chunks of substitution operands, team_plan.h)
     int oval, osv, oalpha;               // shared (PLACE bits 0 / 1) or global
-    int ostate, oring, odynv;            // global
+    int ostate, oring, odynv, osvp;      // global (svp: partial sums of the linear prefixes of the factor entries, nonlinear circuits)
     int sm_doubles, gl_doubles;
 };
 
 // place: bit 0 = slot table in shared memory, bit 1 = factors in shared memory (nonlinear circuits: both are touched in
 // every Newton iteration), bit 2 = the entries of A in the global region (large circuits: read once per iteration)
-__host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_slots, int n_dyn, int n_src, int place)
+__host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_slots, int n_dyn, int n_src, int place, int n_pre = 0)
 {
     TeamLayout t;
     int so = 0, go = 0;
@@ -67,6 +67,7 @@ __host__ __device__ inline TeamLayout team_layout(int n, int nA, int S, int n_sl
     t.ostate = tg(2 * n_dyn);
     t.oring = tg(3 * n);
     t.odynv = tg(n_dyn);
+    t.osvp = tg(n_pre);
     t.sm_doubles = so;
     t.gl_doubles = go > 0 ? go : 1;
     return t;
@@ -131,7 +132,12 @@ struct TeamOps {
             }
         }
     }
-    static __device__ __forceinline__ void assemble_sv(const TeamPlan &P, V val, V sv, int l, bool on)
+    // PRE = 0: the whole contribution list of every static entry.  PRE = 1: only the linear prefixes, into svp (once per attempt
+    // of a nonlinear circuit).  PRE = 2: continue from svp with the contributions behind the prefix (every Newton iteration) —
+    // the same additions in the same order as PRE = 0, without re-summing what cannot have changed (a supply rail's diagonal
+    // entry sums one conductance per stage: 254 dependent loads by one lane in every iteration of an inverter chain).
+    template <int PRE>
+    static __device__ __forceinline__ void assemble_sv(const TeamPlan &P, V val, V sv, V svp, int l, bool on)
     {
         if (on) {
             constexpr int EB = 4; // entries in flight per lane (the slot table may live in L2: overlap the gathers)
@@ -144,8 +150,18 @@ struct TeamOps {
                     const bool oke = e < P.nJ;
                     c0[u] = oke ? __ldg(&P.sptr[e]) : 0;
                     len[u] = oke ? __ldg(&P.sptr[e + 1]) - c0[u] : 0;
-                    maxlen = max(maxlen, len[u]);
                     acc[u] = 0.0;
+                    if (PRE != 0 && oke) {
+                        const int pre = __ldg(&P.spre[e]);
+                        if (PRE == 1)
+                            len[u] = pre;
+                        else {
+                            c0[u] += pre;
+                            len[u] -= pre;
+                            if (pre > 0) acc[u] = svp[e];
+                        }
+                    }
+                    maxlen = max(maxlen, len[u]);
                 }
                 for (int tt = 0; tt < maxlen; ++tt) {
 #pragma unroll
@@ -160,10 +176,11 @@ struct TeamOps {
 #pragma unroll
                 for (int u = 0; u < EB; ++u) {
                     const int e = e0 + u * G;
-                    if (e < P.nJ) sv[e] = acc[u];
+                    if (e < P.nJ) (PRE == 1 ? svp : sv)[e] = acc[u];
                 }
             }
-            for (int e = P.nJ + l; e < P.S; e += G) sv[e] = 0.0;
+            if (PRE != 1)
+                for (int e = P.nJ + l; e < P.S; e += G) sv[e] = 0.0;
         }
     }
 
@@ -549,82 +566,81 @@ struct TeamOps {
         return !any(bad, tmask);
     }
 
-    // ---- level schedules (team_plan.h): the ops of a level on the lanes of the team, a warp barrier between levels ----
-    static __device__ bool factor_levels(const TeamPlan &P, V sv, V alpha, int l, bool on, unsigned tmask)
+    // ---- level schedules (team_plan.h): the ops of a level on the lanes of the team, a warp barrier between levels.  The level
+    // pointers are loaded two levels ahead and each lane's first op word of the NEXT level one level ahead, so that on the narrow
+    // levels of a recurrence (one or two ops) no global load sits between two barriers.
+    template <class F>
+    static __device__ __forceinline__ void level_walk(const int *lptr, const int2 *ops, int nlev, int l, F &&exec)
     {
-        bool bad = false;
-        const int2 *ops = reinterpret_cast<const int2 *>(P.xlop);
-        const int nlev = P.nXlev;
-        int o0 = __ldg(&P.xlptr[0]), o1 = __ldg(&P.xlptr[1]);
+        if (nlev <= 0) return;
+        int o0 = __ldg(&lptr[0]), o1 = __ldg(&lptr[1]);
+        int o2 = nlev >= 2 ? __ldg(&lptr[2]) : o1;
+        int2 wn = o0 + l < o1 ? __ldg(ops + o0 + l) : make_int2(0, 0);
         for (int L = 0; L < nlev; ++L) {
-            const int o2 = L + 2 <= nlev ? __ldg(&P.xlptr[L + 2]) : o1; // (one level ahead: off the critical path)
-            for (int o = o0 + l; o < o1; o += G) {
-                const int2 w = __ldg(ops + o);
-                if (on) {
-                    if (w.y < 0)
-                        bad |= step_head(P, sv, alpha, w.x);
-                    else {
-                        const double m = sv[w.y];
-                        if (m != 0.0) { // a - 0 * p == a
-                            const int d = w.x & 0xffff, s_ = (w.x >> 16) & 0xffff;
-                            sv[d] = sv[d] - m * sv[s_]; // (:35-39)
-                        }
-                    }
-                }
+            const int o3 = L + 3 <= nlev ? __ldg(&lptr[L + 3]) : o2;
+            const int2 w0 = wn;
+            if (L + 1 < nlev) wn = o1 + l < o2 ? __ldg(ops + o1 + l) : make_int2(0, 0);
+            if (o0 + l < o1) {
+                exec(w0);
+                for (int o = o0 + l + G; o < o1; o += G) exec(__ldg(ops + o));
             }
             __syncwarp();
             o0 = o1;
             o1 = o2;
+            o2 = o3;
         }
+    }
+    static __device__ bool factor_levels(const TeamPlan &P, V sv, V alpha, V y, int l, bool on, unsigned tmask)
+    {
+        bool bad = false;
+        level_walk(P.xlptr, reinterpret_cast<const int2 *>(P.xlop), P.nXlev, l, [&](const int2 w) {
+            if (on) {
+                if (w.y < 0)
+                    bad |= step_head(P, sv, alpha, w.x);
+                else if (w.y & 0x40000000) { // forward substitution op (gauss_lu.rs:40)
+                    const double m = sv[w.y & 0xffff];
+                    if (m != 0.0) {
+                        const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
+                        y[r] = y[r] - m * y[pk];
+                    }
+                } else {
+                    const double m = sv[w.y];
+                    if (m != 0.0) { // a - 0 * p == a
+                        const int d = w.x & 0xffff, s_ = (w.x >> 16) & 0xffff;
+                        sv[d] = sv[d] - m * sv[s_]; // (:35-39)
+                    }
+                }
+            }
+        });
         return any(on && bad, tmask);
     }
     static __device__ void forward_levels(const TeamPlan &P, V sv, V y, int l, bool on)
     {
-        const int2 *ops = reinterpret_cast<const int2 *>(P.flop);
-        const int nlev = P.nFlev;
-        int o0 = __ldg(&P.flptr[0]), o1 = __ldg(&P.flptr[1]);
-        for (int L = 0; L < nlev; ++L) {
-            const int o2 = L + 2 <= nlev ? __ldg(&P.flptr[L + 2]) : o1;
-            for (int o = o0 + l; o < o1; o += G) {
-                const int2 w = __ldg(ops + o);
-                if (on) {
-                    const double m = sv[w.y];
-                    if (m != 0.0) {
-                        const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
-                        y[r] = y[r] - m * y[pk]; // (:40)
-                    }
+        level_walk(P.flptr, reinterpret_cast<const int2 *>(P.flop), P.nFlev, l, [&](const int2 w) {
+            if (on) {
+                const double m = sv[w.y];
+                if (m != 0.0) {
+                    const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
+                    y[r] = y[r] - m * y[pk]; // (:40)
                 }
             }
-            __syncwarp();
-            o0 = o1;
-            o1 = o2;
-        }
+        });
     }
     static __device__ bool backward_levels(const TeamPlan &P, V sv, V alpha, V y, V xp, int l, bool on, unsigned tmask)
     {
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         bool bad = false;
-        const int2 *ops = reinterpret_cast<const int2 *>(P.blop);
-        const int nlev = P.nBlev;
-        int o0 = __ldg(&P.blptr[0]), o1 = __ldg(&P.blptr[1]);
-        for (int L = 0; L < nlev; ++L) {
-            const int o2 = L + 2 <= nlev ? __ldg(&P.blptr[L + 2]) : o1;
-            for (int o = o0 + l; o < o1; o += G) {
-                const int2 w = __ldg(ops + o);
-                if (on) {
-                    const int row = w.x & 0xffff, i = (w.x >> 16) & 0xffff;
-                    if (w.y < 0) { // x_i = y[pivot row] / pivot (gauss_lu.rs:47)
-                        const double xi = div_known_rcp(y[row], sv[w.y & 0xffff], alpha[i]);
-                        xp[i] = xi;
-                        bad |= !(fabs(xi) < INF);
-                    } else // y[r] -= x_i * u(r, i) (:49-52)
-                        y[row] = y[row] - xp[i] * sv[w.y];
-                }
+        level_walk(P.blptr, reinterpret_cast<const int2 *>(P.blop), P.nBlev, l, [&](const int2 w) {
+            if (on) {
+                const int row = w.x & 0xffff, i = (w.x >> 16) & 0xffff;
+                if (w.y < 0) { // x_i = y[pivot row] / pivot (gauss_lu.rs:47)
+                    const double xi = div_known_rcp(y[row], sv[w.y & 0xffff], alpha[i]);
+                    xp[i] = xi;
+                    bad |= !(fabs(xi) < INF);
+                } else // y[r] -= x_i * u(r, i) (:49-52)
+                    y[row] = y[row] - xp[i] * sv[w.y];
             }
-            __syncwarp();
-            o0 = o1;
-            o1 = o2;
-        }
+        });
         return !any(on && bad, tmask);
     }
 
@@ -675,7 +691,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
     const V stg{sw + L.ostg * T};
     const V val{((PLACE & 1) ? sw : gw) + L.oval * T};
     const V sv{((PLACE & 2) ? sw : gw) + L.osv * T}, alpha{((PLACE & 2) ? sw : gw) + L.oalpha * T};
-    const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T};
+    const V state{gw + L.ostate * T}, ring{gw + L.oring * T}, dynv{gw + L.odynv * T}, svp{gw + L.osvp * T};
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const bool linear = RC > 0 || M.n_nl == 0;                       // (RC > 0: guaranteed by the launcher, as is the chain plan)
     const bool chain = RC > 0 || (P.chain != 0 && G <= TEAM_CHUNK); // single-lane op streams (ladders); wider teams: lane-parallel lists
@@ -820,8 +836,9 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
             const bool mchg = act && h_first != hA; // the companion conductances changed: A (and, linear, its factors)
             if (__any_sync(0xffffffffu, mchg)) {
                 Ops::assemble(P, val, A, sv, l, mchg);
+                if (!linear) Ops::template assemble_sv<1>(P, val, sv, svp, l, mchg); // the linear prefixes of the factor entries
                 if (linear) {
-                    Ops::assemble_sv(P, val, sv, l, mchg);
+                    Ops::template assemble_sv<0>(P, val, sv, svp, l, mchg);
                     __syncwarp();
                     if (Ops::factor(P, sv, alpha, l, mchg, tmask)) redo = true;
                     if (mchg) {
@@ -1022,11 +1039,11 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                 if (!linear) {
                     if (it_on)
                         for (int i = l; i < n; i += G) y[i] = Ops::gsum(M.r_nl, i, val, b[i]);
-                    Ops::assemble_sv(P, val, sv, l, it_on);
+                    Ops::template assemble_sv<2>(P, val, sv, svp, l, it_on);
                     __syncwarp();
                     if constexpr ((PLACE & 2) != 0) { // factors in shared memory: early steps in parallel, then one op stream
                         if (P.levels) { // level schedules: all lanes of the team, a barrier per level
-                            if (Ops::factor_levels(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;
+                            if (Ops::factor_levels(P, sv, alpha, y, l, it_on, tmask) && it_on) redo = true;
                             Ops::forward_levels(P, sv, y, l, it_on);
                             if (!Ops::backward_levels(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
                         } else { // early steps in parallel, then one lane walks the rest

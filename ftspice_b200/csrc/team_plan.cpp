@@ -19,6 +19,7 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.acon = b + o_acon;
     p.sptr = b + o_sptr;
     p.scon = b + o_scon;
+    p.spre = b + o_spre;
     p.pivrow = b + o_pivrow;
     p.pive = b + o_pive;
     p.tptr = b + o_tptr;
@@ -174,6 +175,18 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
         rows[dst & 0xffff][dst >> 16] = d;
     }
     std::vector<int> sptr(ib.begin() + jf.ptr, ib.begin() + jf.ptr + nJ + 1), scon(ib.begin() + jf.con, ib.begin() + jf.con + jf.n_con);
+    // linear prefix of every static entry: the contributions it shares, in order, with the entry of A (A's list is J's list
+    // without the nonlinear stamps)
+    std::vector<int> spre(nJ, 0);
+    for (int d = 0; d < nJ; ++d) {
+        const int dst = ib[jf.dst + d], key = ((dst & 0xffff) << 16) | (dst >> 16);
+        auto it = a_ent.find(key);
+        if (it == a_ent.end()) continue;
+        const std::vector<int> &av = it->second;
+        int k = 0;
+        while (sptr[d] + k < sptr[d + 1] && k < (int)av.size() && scon[sptr[d] + k] == av[k]) ++k;
+        spre[d] = k;
+    }
     int S = nJ;
     std::vector<int> pos(n), piv(n);
     for (int i = 0; i < n; ++i) pos[i] = piv[i] = i;
@@ -350,22 +363,24 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
                         ops.push_back(up);
                     }
             }
-            levelize(ops, S + n, lptr, words);
-            out.nXlev = (int)lptr.size() - 1;
-            out.o_xlptr = push2(lptr);
-            out.o_xlop = push2(words);
-            ops.clear();
+            // the forward substitution rides along (the right-hand side as one more column): its ops only need their multiplier
+            // and the final y of the pivot row, so they fill the same levels as the elimination instead of 256 levels of their own
             for (int k = 0; k < n; ++k)
                 for (int tt = tptr[k]; tt < tptr[k + 1]; ++tt) {
                     LevOp f;
                     f.w0 = tgtr[tt] | (pivrow[k] << 16);
-                    f.w1 = tgt[tt] & 0xffff;
-                    f.reads = {tgtr[tt], pivrow[k]};
-                    f.writes = {tgtr[tt]};
+                    f.w1 = (tgt[tt] & 0xffff) | 0x40000000;
+                    f.reads = {tgt[tt] & 0xffff, S + n + tgtr[tt], S + n + pivrow[k]};
+                    f.writes = {S + n + tgtr[tt]};
                     ops.push_back(f);
                 }
-            levelize(ops, n, lptr, words);
-            out.nFlev = (int)lptr.size() - 1;
+            levelize(ops, S + 2 * n, lptr, words);
+            out.nXlev = (int)lptr.size() - 1;
+            out.o_xlptr = push2(lptr);
+            out.o_xlop = push2(words);
+            out.nFlev = 0; // (kept in the interface: a separate forward schedule)
+            lptr.assign(1, 0);
+            words.clear();
             out.o_flptr = push2(lptr);
             out.o_flop = push2(words);
             ops.clear();
@@ -413,6 +428,7 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
     out.o_acon = push(acon);
     out.o_sptr = push(sptr);
     out.o_scon = push(scon);
+    out.o_spre = push(spre);
     out.o_pivrow = push(pivrow);
     out.o_pive = push(pive);
     out.o_tptr = push(tptr);

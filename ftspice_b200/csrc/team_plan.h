@@ -24,6 +24,8 @@ struct TeamPlan {
     const int *acon;
     const int *sptr;        // [nJ + 1] contributions of the static entries of J (all phases); fill-in entries start at 0.0
     const int *scon;
+    const int *spre;        // [nJ] leading contributions of the entry that are linear / companion stamps (they do not change inside a
+                            //      Newton call): their partial sum is kept per attempt and the per-iteration gather starts behind them
     const int *pivrow;      // [n] pivot row of step k
     const int *pive;        // [n] its entry in column k
     const int *tptr;        // [n + 1] targets (rows eliminated) of step k
@@ -77,7 +79,8 @@ struct TeamPlan {
     //      the same order as in the sequential streams, so the results are the same bits.  An inverter chain: 765 elimination
     //      ops in 256 levels (all 257 early heads at once, then the rail recurrence), forward 509 ops in 256 levels, backward
     //      512 ops in THREE levels (x_rail, all updates, all divides) instead of one lane walking 1 786 dependent ops.
-    //      xlop: as xop.  flop: as dfop.  blop: divide as dbop; update: word0 = row r | column i << 16 (x_i is read from
+    //      xlop: as xop, plus the FORWARD ops (word1 bit 30 set: word0 = row r | pivot row << 16, word1 & 0xffff = multiplier
+    //      entry) — the right-hand side is eliminated along with the matrix; flop: a separate forward schedule (empty).  blop: divide as dbop; update: word0 = row r | column i << 16 (x_i is read from
     //      x_proposed), word1 = entry of U.
     int levels;             // 1: use them (option team_levels)
     int nXlev, nFlev, nBlev;
@@ -91,7 +94,7 @@ constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging pe
 struct TeamPlanHost {
     int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0;
     std::vector<int> ibuf;
-    int o_arow = 0, o_acol = 0, o_aptr = 0, o_acon = 0, o_sptr = 0, o_scon = 0, o_pivrow = 0, o_pive = 0, o_tptr = 0, o_tgt = 0,
+    int o_arow = 0, o_acol = 0, o_aptr = 0, o_acon = 0, o_sptr = 0, o_scon = 0, o_spre = 0, o_pivrow = 0, o_pive = 0, o_tptr = 0, o_tgt = 0,
         o_tgtr = 0, o_uptr = 0, o_updm = 0, o_updds = 0, o_bptr = 0, o_bwde = 0, o_bwdr = 0;
     int ellW = 0, nSlotA = 0, o_ellcol = 0, o_ovfptr = 0, o_ovfcol = 0;
     int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,

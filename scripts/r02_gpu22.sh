@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "mid_size or sparse_kernel or tran_inverter or inverter or c5" > gpurun_out/g22_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/g22_tests.log; tail -n 5 gpurun_out/g22_tests.log
 i=0
-for opts in "--opt team_place=6" "--opt team_place=6 --opt team_levels=0" ""; do
+for opts in "--opt team_place=6"; do
   i=$((i+1))
   timeout 900 python bench.py --workload c5 --scale 0.25 --steps 2 --warmup 3 --no-cpu $opts > gpurun_out/g22_$i.json 2> gpurun_out/g22_$i.err
   echo "[$opts] rc=$?"; python -c "

@@ -70,8 +70,12 @@ def team_plan(circ, an=2):
     for k, v in zip(["nXlev", "nFlev", "nBlev"], meta[49:52]):
         p[k] = int(v)
     for k, o, ln in zip(["xlptr", "xlop", "flptr", "flop", "blptr", "blop"], meta[52:58],
-                        [p["nXlev"] + 1, 2 * (p["n"] + p["nU"]), p["nFlev"] + 1, 2 * p["nDFop"], p["nBlev"] + 1, 2 * p["nDBop"]]):
+                        [p["nXlev"] + 1, 2 * (p["n"] + p["nU"] + p["nDFop"]), p["nFlev"] + 1, 0, p["nBlev"] + 1, 2 * p["nDBop"]]):
         p[k] = ibuf[int(o):int(o) + ln].copy()
+    p["spre"] = ibuf[int(meta[58]):int(meta[58]) + p["nJ"]].copy()
+    p["scon"] = ibuf[int(meta[12]):int(meta[12]) + int(p["sptr"][-1])].copy()
+    p["aptr"] = ibuf[int(meta[9]):int(meta[9]) + p["nSlotA"] + 1].copy()  # indexed by ELL slot (padding slots: empty lists)
+    p["acon"] = ibuf[int(meta[10]):int(meta[10]) + int(p["aptr"][-1])].copy()
     p["jdst"] = jdst[:p["nJ"]].copy()
     p["piv"] = piv[:p["n"]].copy()
     return p
@@ -171,7 +175,7 @@ def run_levels(p, vals, rhs, rng):
     x = np.full(n, np.nan)
 
     def walk(lptr, ops, nops, exec_op, arrays):
-        assert lptr[0] == 0 and lptr[-1] == nops and np.all(np.diff(lptr) > 0)
+        assert lptr[0] == 0 and lptr[-1] == nops and np.all(np.diff(lptr) > 0), (lptr[-1], nops)
         for L in range(len(lptr) - 1):
             snap = [a.copy() for a in arrays]  # operands as they stood at the barrier
             writes = {}
@@ -182,9 +186,14 @@ def run_levels(p, vals, rhs, rng):
             for (ai, idx), v in writes.items():
                 arrays[ai][idx] = v
 
-    def x_op(w0, w1, sv_, alpha_):
+    def x_op(w0, w1, sv_, alpha_, y_):
         out = []
-        if w1 < 0:
+        if w1 >= 0 and (w1 & 0x40000000):  # forward substitution op riding along with the elimination
+            m = sv_[w1 & 0xffff]
+            if m != 0.0:
+                r, pk = w0 & 0xffff, (w0 >> 16) & 0xffff
+                out.append(((2, r), y_[r] - m * y_[pk]))
+        elif w1 < 0:
             k = w0
             al = np.float64(1.0) / sv_[p["pive"][k]]
             out.append(((1, k), al))
@@ -198,7 +207,7 @@ def run_levels(p, vals, rhs, rng):
                 out.append(((0, d), sv_[d] - m * sv_[s_]))
         return out
 
-    walk(p["xlptr"], p["xlop"], p["n"] + p["nU"], x_op, [sv, alpha])  # every head + every update
+    walk(p["xlptr"], p["xlop"], p["n"] + p["nU"] + p["nDFop"], x_op, [sv, alpha, y])  # every head, update and forward op
 
     def f_op(w0, w1, y_):
         m = sv[w1]
@@ -207,7 +216,7 @@ def run_levels(p, vals, rhs, rng):
             return [((0, r), y_[r] - m * y_[pk])]
         return []
 
-    walk(p["flptr"], p["flop"], p["nDFop"], f_op, [y])
+    assert p["nFlev"] == 0  # (a separate forward schedule: unused)
 
     def b_op(w0, w1, y_, x_):
         row, i = w0 & 0xffff, (w0 >> 16) & 0xffff
@@ -373,3 +382,36 @@ def test_team_exact_division_equals_plain_division_bitwise():
         with np.errstate(all="ignore"):
             host = y / d
         assert ((ref.view(np.uint64) == host.view(np.uint64)) | (np.isnan(ref) & np.isnan(host))).all()
+
+
+@pytest.mark.parametrize("which", ["inverter40", "inverter258", "ladder64"])
+def test_linear_prefix_of_the_factor_entries(which):
+    """spre[e] = how many leading contributions of static entry e are linear / companion stamps: exactly the contributions
+    of A's entry at the same position, in the same order (the per-attempt partial sum the Newton iterations start from)."""
+    p = team_plan(nl.load(CIRCUITS[which]()))
+    n, W = p["n"], p["ellW"]
+    a_list = {}
+    ovf = 0
+    for r in range(n):
+        cols = [int(p["acol"][c]) for c in range(p["arow"][r], p["arow"][r + 1])]
+        for w, c in enumerate(cols):
+            if w < W:
+                slot = r * W + w
+            else:
+                slot = W * (n + 1) + ovf
+                ovf += 1
+            a_list[(r, c)] = p["acon"][p["aptr"][slot]:p["aptr"][slot + 1]].tolist()
+    longest = 0
+    for d in range(p["nJ"]):
+        r, c = int(p["jdst"][d]) & 0xffff, int(p["jdst"][d]) >> 16
+        full = p["scon"][p["sptr"][d]:p["sptr"][d + 1]].tolist()
+        k = int(p["spre"][d])
+        al = a_list.get((r, c), [])
+        assert full[:k] == al[:k]
+        assert k == len(full) or k == len(al) or full[k] != al[k]
+        assert [w for w in full if w in al] == al  # A's list is J's list without the nonlinear stamps, in order
+        longest = max(longest, k)
+    if which == "inverter258":
+        assert longest >= 254  # the rail's diagonal entry: one conductance per stage
+    if which == "ladder64":
+        assert all(int(p["spre"][d]) == p["sptr"][d + 1] - p["sptr"][d] for d in range(p["nJ"]))  # linear circuit
