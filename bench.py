@@ -12,7 +12,7 @@ instance, 6.6e8 solve-points per GPU) takes ~12 s per pass, so one timed step ru
 of it (1.08 us, ~2070 accepted steps per instance, start-up .op and the h ramp-up included); `--full-span` times the whole span instead
 (the full-span numbers of the round are committed under profiles/).  `configs` holds the other named configs measured in
 the same run, each with its own roofline / cpu_baseline / e2e: C2 (.op, 65 536 instances per GPU), C3 (.dc, 1 M sweep
-points in total) and C5 (.tran, 256-node inverter chain, 16 384 instances in total, 4 ns of the 168 ns span per step).
+points in total) and C5 (.tran, 256-node inverter chain, 16 384 instances in total, 12 ns of the 168 ns span per step).
 
 `value` = solve-points/s with the parameters already resident in HBM (device pointers through the C-ABI); `e2e` = the
 same through the C-ABI with pinned HOST buffers, host->device and device->host copies inside the timed region.  One
@@ -79,9 +79,9 @@ def make_workload(name: str, scale: float, world: int, full_span: bool = False, 
                           f"every step runs all instances from t=0 over {span}")
     if name == "c5":
         circ = nl.load(nl.inverter_chain_netlist(256, stop="168n", step="50p"))
-        stop = tran_stop or (168e-9 if full_span else 4e-9)
+        stop = tran_stop or (168e-9 if full_span else 12e-9)
         total = max(world, int(16384 * scale))
-        span = "the full named span" if stop == 168e-9 else f"{stop:g}s of the named 168ns span per step (through the input's rising edge)"
+        span = "the full named span" if stop == 168e-9 else f"{stop:g}s of the named 168ns span per step (through the input's first pulse; the start-up .op of every instance is inside the step)"
         return dict(name="c5", kind="tran", circ=circ, batch=total // world, stop=stop, step=50e-12, scaling="strong",
                     full_stop=168e-9,
                     label=f"C5 256-node NMOS inverter chain (n=258) .TRAN 50p max step, {total} instances in total sharded over the "

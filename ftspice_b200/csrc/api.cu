@@ -795,18 +795,19 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
     const TeamPlanHost &ph = c->team_plan;
     const bool linear = mo.n_nl == 0;
     // placement: a linear circuit touches its slot table and factors once per attempt (global scratch); a nonlinear one in
-    // every Newton iteration (shared memory).  A circuit too large for that (n = 258: 54 KB per instance) can run with
-    // only the factors and the vectors in shared memory (option team_place = 6: slot table and entries of A in the
-    // scratch, elimination as early steps + one op stream) — measured SLOWER than the warp kernel's windowed elimination
-    // on the C5 chain (0.22 vs 0.28 M solve-points/s on 4 096 instances x 4 ns: one lane walks ~1 550 dependent ops per
-    // Newton iteration), so it is not chosen automatically
+    // every Newton iteration (shared memory: placement 3).  A circuit too large for that (n = 258: 54 KB per instance) runs
+    // with only the factors and the vectors in shared memory (placement 6: slot table and entries of A in the scratch).  With
+    // one lane walking the ~1 550 dependent ops of a Newton iteration that was slower than the warp kernel's windowed
+    // elimination on the C5 chain (0.22 vs 0.28 M solve-points/s on 4 096 instances x 4 ns); with the level schedules, the
+    // linear-prefix sums and the forward substitution merged into the elimination it is faster (0.39 M) and is tried
+    // automatically when placement 3 does not fit
     int place = 0;
     // lanes per instance: rows are dealt round-robin, so few lanes waste little; more teams per warp amortise the
     // list-walking code over more instances but need more shared memory per warp
     int best_g = 0, best_occ = 0, best_wpb = 0, best_rows = 0;
     size_t best_smem = 0;
     TeamLayout best_lay{};
-    for (int place_try : {c->team_place >= 0 ? (c->team_place & 7) : (linear ? 0 : 3), -1}) {
+    for (int place_try : {c->team_place >= 0 ? (c->team_place & 7) : (linear ? 0 : 3), c->team_place >= 0 || linear ? -1 : 6, -1}) {
     if (place_try < 0 || best_g) break;
     place = place_try;
     for (int g : {8, 16, 32}) {
