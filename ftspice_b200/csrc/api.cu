@@ -824,7 +824,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
         }
         if (fn) {
             const int T = 32 / g;
-            const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place, linear ? 0 : ph.nJ);
+            const TeamLayout lay = team_layout(mo.n, ph.nSlotA, ph.S, c->comp.n_slots, c->comp.n_dyn, c->comp.n_src, place, linear ? 0 : ph.nPre);
             int w_best = 0, occ_best = 0;
             size_t smem_best = 0;
             for (int wpb = rows ? TEAM_WARPS_ROWS : TEAM_WARPS_MAX; wpb >= 1; --wpb) { // warps per block: whatever packs most warps onto an SM

@@ -142,7 +142,7 @@ struct TeamOps {
         if (on) {
             constexpr int EB = 4; // entries in flight per lane (the slot table may live in L2: overlap the gathers)
             for (int e0 = l; e0 < P.nJ; e0 += EB * G) {
-                int c0[EB], len[EB], maxlen = 0;
+                int c0[EB], len[EB], pix[EB], maxlen = 0;
                 double acc[EB];
 #pragma unroll
                 for (int u = 0; u < EB; ++u) {
@@ -151,14 +151,16 @@ struct TeamOps {
                     c0[u] = oke ? __ldg(&P.sptr[e]) : 0;
                     len[u] = oke ? __ldg(&P.sptr[e + 1]) - c0[u] : 0;
                     acc[u] = 0.0;
+                    pix[u] = -1;
                     if (PRE != 0 && oke) {
-                        const int pre = __ldg(&P.spre[e]);
-                        if (PRE == 1)
+                        const int pw = __ldg(&P.spre[e]), pre = pw >> 16;
+                        if (PRE == 1) {
                             len[u] = pre;
-                        else {
+                            if (pre > 0) pix[u] = pw & 0xffff;
+                        } else if (pre > 0) {
                             c0[u] += pre;
                             len[u] -= pre;
-                            if (pre > 0) acc[u] = svp[e];
+                            acc[u] = svp[pw & 0xffff];
                         }
                     }
                     maxlen = max(maxlen, len[u]);
@@ -176,7 +178,10 @@ struct TeamOps {
 #pragma unroll
                 for (int u = 0; u < EB; ++u) {
                     const int e = e0 + u * G;
-                    if (e < P.nJ) (PRE == 1 ? svp : sv)[e] = acc[u];
+                    if (PRE == 1) {
+                        if (pix[u] >= 0) svp[pix[u]] = acc[u];
+                    } else if (e < P.nJ)
+                        sv[e] = acc[u];
                 }
             }
             if (PRE != 1)

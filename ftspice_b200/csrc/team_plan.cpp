@@ -20,6 +20,7 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.sptr = b + o_sptr;
     p.scon = b + o_scon;
     p.spre = b + o_spre;
+    p.nPre = nPre;
     p.pivrow = b + o_pivrow;
     p.pive = b + o_pive;
     p.tptr = b + o_tptr;
@@ -185,7 +186,9 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
         const std::vector<int> &av = it->second;
         int k = 0;
         while (sptr[d] + k < sptr[d + 1] && k < (int)av.size() && scon[sptr[d] + k] == av[k]) ++k;
-        spre[d] = k;
+        // a prefix of one contribution costs a load either way: kept sums only from two on, numbered compactly (the sums
+        // live in the L2-resident scratch row of the instance)
+        if (k >= 2 && k < 65536 && out.nPre < 65535) spre[d] = (k << 16) | out.nPre++;
     }
     int S = nJ;
     std::vector<int> pos(n), piv(n);

@@ -24,8 +24,10 @@ struct TeamPlan {
     const int *acon;
     const int *sptr;        // [nJ + 1] contributions of the static entries of J (all phases); fill-in entries start at 0.0
     const int *scon;
-    const int *spre;        // [nJ] leading contributions of the entry that are linear / companion stamps (they do not change inside a
-                            //      Newton call): their partial sum is kept per attempt and the per-iteration gather starts behind them
+    const int *spre;        // [nJ] (count << 16 | index): the leading `count` contributions of the entry are linear / companion stamps
+                            //      (they do not change inside a Newton call); their partial sum is kept per attempt at svp[index] and
+                            //      the per-iteration gather starts behind them.  0: no kept sum (fewer than two such contributions)
+    int nPre;               // kept sums
     const int *pivrow;      // [n] pivot row of step k
     const int *pive;        // [n] its entry in column k
     const int *tptr;        // [n + 1] targets (rows eliminated) of step k
@@ -92,7 +94,7 @@ struct TeamPlan {
 constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
 
 struct TeamPlanHost {
-    int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0;
+    int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0, nPre = 0;
     std::vector<int> ibuf;
     int o_arow = 0, o_acol = 0, o_aptr = 0, o_acon = 0, o_sptr = 0, o_scon = 0, o_spre = 0, o_pivrow = 0, o_pive = 0, o_tptr = 0, o_tgt = 0,
         o_tgtr = 0, o_uptr = 0, o_updm = 0, o_updds = 0, o_bptr = 0, o_bwde = 0, o_bwdr = 0;

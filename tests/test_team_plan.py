@@ -401,17 +401,20 @@ def test_linear_prefix_of_the_factor_entries(which):
                 slot = W * (n + 1) + ovf
                 ovf += 1
             a_list[(r, c)] = p["acon"][p["aptr"][slot]:p["aptr"][slot + 1]].tolist()
-    longest = 0
+    longest = seen = 0
     for d in range(p["nJ"]):
         r, c = int(p["jdst"][d]) & 0xffff, int(p["jdst"][d]) >> 16
         full = p["scon"][p["sptr"][d]:p["sptr"][d + 1]].tolist()
-        k = int(p["spre"][d])
+        k, idx = int(p["spre"][d]) >> 16, int(p["spre"][d]) & 0xffff
         al = a_list.get((r, c), [])
         assert full[:k] == al[:k]
-        assert k == len(full) or k == len(al) or full[k] != al[k]
+        if k:  # a kept sum: at least two contributions, the whole common prefix, compact numbering
+            assert k >= 2 and (k == len(full) or k == len(al) or full[k] != al[k])
+            assert idx == seen
+            seen += 1
         assert [w for w in full if w in al] == al  # A's list is J's list without the nonlinear stamps, in order
         longest = max(longest, k)
     if which == "inverter258":
         assert longest >= 254  # the rail's diagonal entry: one conductance per stage
     if which == "ladder64":
-        assert all(int(p["spre"][d]) == p["sptr"][d + 1] - p["sptr"][d] for d in range(p["nJ"]))  # linear circuit
+        assert all((int(p["spre"][d]) >> 16) in (0, p["sptr"][d + 1] - p["sptr"][d]) for d in range(p["nJ"]))  # linear circuit
