@@ -1976,6 +1976,8 @@ extern "C" int ftsb_debug_team_plan(const ftsb_elem *elems, int32_t n_elems, int
     const int m4[] = {ph.nXlev, ph.nFlev, ph.nBlev, ph.o_xlptr, ph.o_xlop, ph.o_flptr, ph.o_flop, ph.o_blptr, ph.o_blop};
     std::copy(m4, m4 + 9, meta + 49); // meta[49..57]: the level schedules
     meta[58] = ph.o_spre;
+    const int m5[] = {ph.nXseg, ph.o_xseg, ph.o_xsop, ph.nBseg, ph.o_bseg, ph.o_bsop};
+    std::copy(m5, m5 + 6, meta + 59); // meta[59..64]: the segmented form of the level schedules (the caller's meta holds >= 96 ints)
     for (int d = 0; d < ph.nJ; ++d) jdst[d] = ib[mo.J_full.dst + d];
     std::copy(pv.begin(), pv.end(), piv);
     return 0;

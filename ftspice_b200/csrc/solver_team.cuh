@@ -575,68 +575,57 @@ struct TeamOps {
     // pointers are loaded two levels ahead and each lane's first op word of the NEXT level one level ahead, so that on the narrow
     // levels of a recurrence (one or two ops) no global load sits between two barriers.
     template <class F>
-    static __device__ __forceinline__ void level_walk(const int *lptr, const int2 *ops, int nlev, int l, F &&exec)
+    static __device__ __forceinline__ void seg_walk(const int *seg, int nseg, const int2 *ops, int l, F &&exec)
     {
-        if (nlev <= 0) return;
-        int o0 = __ldg(&lptr[0]), o1 = __ldg(&lptr[1]);
-        int o2 = nlev >= 2 ? __ldg(&lptr[2]) : o1;
-        int2 wn = o0 + l < o1 ? __ldg(ops + o0 + l) : make_int2(0, 0);
-        for (int L = 0; L < nlev; ++L) {
-            const int o3 = L + 3 <= nlev ? __ldg(&lptr[L + 3]) : o2;
-            const int2 w0 = wn;
-            if (L + 1 < nlev) wn = o1 + l < o2 ? __ldg(ops + o1 + l) : make_int2(0, 0);
-            if (o0 + l < o1) {
-                exec(w0);
-                for (int o = o0 + l + G; o < o1; o += G) exec(__ldg(ops + o));
+        const int2 *sg = reinterpret_cast<const int2 *>(seg);
+        int2 sn = nseg > 0 ? __ldg(sg) : make_int2(0, 0);
+        for (int si = 0; si < nseg; ++si) {
+            const int2 sc = sn;
+            if (si + 1 < nseg) sn = __ldg(sg + si + 1);
+            if (sc.x < 0) { // a wide level
+                const int2 *o = ops + sc.y;
+                for (int k = l; k < -sc.x; k += G) exec(__ldg(o + k));
+                __syncwarp();
+            } else { // a run of narrow levels: the lane's op word of the next level is in flight while this one executes
+                const int2 *o = ops + sc.y + l;
+                const bool mine = l < TEAM_NARROW;
+                int2 wn = mine ? __ldg(o) : make_int2(0, TEAM_OP_NOP);
+                for (int j = 0; j < sc.x; ++j) {
+                    const int2 w = wn;
+                    if (mine && j + 1 < sc.x) wn = __ldg(o + (j + 1) * TEAM_NARROW);
+                    if (mine) exec(w);
+                    __syncwarp();
+                }
             }
-            __syncwarp();
-            o0 = o1;
-            o1 = o2;
-            o2 = o3;
         }
     }
+    // elimination + forward substitution (the right-hand side as one more column).  An update and a forward op are the same
+    // statement on different arrays — d -= m * s — so they share one code path (the arrays sit in the same shared memory).
     static __device__ bool factor_levels(const TeamPlan &P, V sv, V alpha, V y, int l, bool on, unsigned tmask)
     {
         bool bad = false;
-        level_walk(P.xlptr, reinterpret_cast<const int2 *>(P.xlop), P.nXlev, l, [&](const int2 w) {
+        seg_walk(P.xseg, P.nXseg, reinterpret_cast<const int2 *>(P.xsop), l, [&](const int2 w) {
             if (on) {
                 if (w.y < 0)
                     bad |= step_head(P, sv, alpha, w.x);
-                else if (w.y & 0x40000000) { // forward substitution op (gauss_lu.rs:40)
+                else if (!(w.y & TEAM_OP_NOP)) {
                     const double m = sv[w.y & 0xffff];
-                    if (m != 0.0) {
-                        const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
-                        y[r] = y[r] - m * y[pk];
-                    }
-                } else {
-                    const double m = sv[w.y];
                     if (m != 0.0) { // a - 0 * p == a
+                        const V t{(w.y & TEAM_OP_FWD) ? y.p : sv.p};
                         const int d = w.x & 0xffff, s_ = (w.x >> 16) & 0xffff;
-                        sv[d] = sv[d] - m * sv[s_]; // (:35-39)
+                        t[d] = t[d] - m * t[s_]; // (:35-39, :40)
                     }
                 }
             }
         });
         return any(on && bad, tmask);
     }
-    static __device__ void forward_levels(const TeamPlan &P, V sv, V y, int l, bool on)
-    {
-        level_walk(P.flptr, reinterpret_cast<const int2 *>(P.flop), P.nFlev, l, [&](const int2 w) {
-            if (on) {
-                const double m = sv[w.y];
-                if (m != 0.0) {
-                    const int r = w.x & 0xffff, pk = (w.x >> 16) & 0xffff;
-                    y[r] = y[r] - m * y[pk]; // (:40)
-                }
-            }
-        });
-    }
     static __device__ bool backward_levels(const TeamPlan &P, V sv, V alpha, V y, V xp, int l, bool on, unsigned tmask)
     {
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
         bool bad = false;
-        level_walk(P.blptr, reinterpret_cast<const int2 *>(P.blop), P.nBlev, l, [&](const int2 w) {
-            if (on) {
+        seg_walk(P.bseg, P.nBseg, reinterpret_cast<const int2 *>(P.bsop), l, [&](const int2 w) {
+            if (on && !(w.y >= 0 && (w.y & TEAM_OP_NOP))) {
                 const int row = w.x & 0xffff, i = (w.x >> 16) & 0xffff;
                 if (w.y < 0) { // x_i = y[pivot row] / pivot (gauss_lu.rs:47)
                     const double xi = div_known_rcp(y[row], sv[w.y & 0xffff], alpha[i]);
@@ -1048,8 +1037,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                     __syncwarp();
                     if constexpr ((PLACE & 2) != 0) { // factors in shared memory: early steps in parallel, then one op stream
                         if (P.levels) { // level schedules: all lanes of the team, a barrier per level
-                            if (Ops::factor_levels(P, sv, alpha, y, l, it_on, tmask) && it_on) redo = true;
-                            Ops::forward_levels(P, sv, y, l, it_on);
+                            if (Ops::factor_levels(P, sv, alpha, y, l, it_on, tmask) && it_on) redo = true; // (+ forward substitution)
                             if (!Ops::backward_levels(P, sv, alpha, y, xp, l, it_on, tmask) && it_on) redo = true;
                         } else { // early steps in parallel, then one lane walks the rest
                             if (Ops::factor_direct(P, sv, alpha, l, it_on, tmask) && it_on) redo = true;

@@ -66,6 +66,12 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.flop = b + o_flop;
     p.blptr = b + o_blptr;
     p.blop = b + o_blop;
+    p.nXseg = nXseg;
+    p.nBseg = nBseg;
+    p.xseg = b + o_xseg;
+    p.xsop = b + o_xsop;
+    p.bseg = b + o_bseg;
+    p.bsop = b + o_bsop;
     return p;
 }
 
@@ -98,6 +104,41 @@ void levelize(const std::vector<LevOp> &ops, int nloc, std::vector<int> &lptr, s
         const int at = cur[lev[o] - 1]++;
         words[2 * at] = ops[o].w0;
         words[2 * at + 1] = ops[o].w1;
+    }
+}
+// The level schedule in the form the kernel walks (team_plan.h): maximal runs of NARROW levels (at most TEAM_NARROW ops) are
+// stored padded to TEAM_NARROW slots per level (padding: the no-op word), every WIDE level as its plain op list.
+void segment(const std::vector<int> &lptr, const std::vector<int> &words, std::vector<int> &seg, std::vector<int> &pops)
+{
+    seg.clear();
+    pops.clear();
+    const int nlev = (int)lptr.size() - 1;
+    int L = 0;
+    while (L < nlev) {
+        const int cnt = lptr[L + 1] - lptr[L];
+        if (cnt > TEAM_NARROW) {
+            seg.push_back(-cnt);
+            seg.push_back((int)pops.size() / 2);
+            pops.insert(pops.end(), words.begin() + 2 * lptr[L], words.begin() + 2 * lptr[L + 1]);
+            ++L;
+            continue;
+        }
+        int L1 = L;
+        while (L1 < nlev && lptr[L1 + 1] - lptr[L1] <= TEAM_NARROW) ++L1;
+        seg.push_back(L1 - L);
+        seg.push_back((int)pops.size() / 2);
+        for (int j = L; j < L1; ++j)
+            for (int k = 0; k < TEAM_NARROW; ++k) {
+                const int o = lptr[j] + k;
+                if (o < lptr[j + 1]) {
+                    pops.push_back(words[2 * o]);
+                    pops.push_back(words[2 * o + 1]);
+                } else {
+                    pops.push_back(0);
+                    pops.push_back(TEAM_OP_NOP);
+                }
+            }
+        L = L1;
     }
 }
 } // namespace
@@ -381,6 +422,13 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
             out.nXlev = (int)lptr.size() - 1;
             out.o_xlptr = push2(lptr);
             out.o_xlop = push2(words);
+            {
+                std::vector<int> seg, pops;
+                segment(lptr, words, seg, pops);
+                out.nXseg = (int)seg.size() / 2;
+                out.o_xseg = push2(seg);
+                out.o_xsop = push2(pops);
+            }
             out.nFlev = 0; // (kept in the interface: a separate forward schedule)
             lptr.assign(1, 0);
             words.clear();
@@ -407,6 +455,13 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
             out.nBlev = (int)lptr.size() - 1;
             out.o_blptr = push2(lptr);
             out.o_blop = push2(words);
+            {
+                std::vector<int> seg, pops;
+                segment(lptr, words, seg, pops);
+                out.nBseg = (int)seg.size() / 2;
+                out.o_bseg = push2(seg);
+                out.o_bsop = push2(pops);
+            }
         }
         out.o_ellcol = push2(ellcol);
         out.o_ovfptr = push2(ovfptr);

@@ -89,7 +89,16 @@ struct TeamPlan {
     const int *xlptr, *xlop; // [nXlev + 1], [nXop][2] sorted by level
     const int *flptr, *flop;
     const int *blptr, *blop;
+    // ---- the same schedules as the kernel walks them: segments (count, offset) — count > 0: a run of `count` NARROW levels (at
+    //      most TEAM_NARROW ops each) stored padded to TEAM_NARROW op slots per level (padding: word1 = TEAM_OP_NOP), so that a
+    //      lane's op word of level j sits at offset + j * TEAM_NARROW + lane and is fetched one level ahead without pointer
+    //      chasing; count < 0: one WIDE level of -count ops.
+    int nXseg, nBseg;
+    const int *xseg, *xsop; // [nXseg][2], [..][2]
+    const int *bseg, *bsop;
 };
+constexpr int TEAM_NARROW = 4;
+constexpr int TEAM_OP_NOP = 0x20000000, TEAM_OP_FWD = 0x40000000;
 
 constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
 
@@ -102,6 +111,7 @@ struct TeamPlanHost {
     int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,
         o_bchunk = 0;
     int nEarly = 0, nXop = 0, nDFop = 0, nDBop = 0, o_early = 0, o_xop = 0, o_dfop = 0, o_dbop = 0;
+    int nXseg = 0, nBseg = 0, o_xseg = 0, o_xsop = 0, o_bseg = 0, o_bsop = 0;
     int nXlev = 0, nFlev = 0, nBlev = 0, o_xlptr = 0, o_xlop = 0, o_flptr = 0, o_flop = 0, o_blptr = 0, o_blop = 0;
     long long flops_factor = 0, flops_solve = 0; // floating-point operations of one factorisation / one pair of substitutions
     TeamPlan view(const int *base) const;

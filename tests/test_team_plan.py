@@ -38,7 +38,7 @@ def team_plan(circ, an=2):
     cls = np.ascontiguousarray(circ.cls, np.int32)
     cap = 1 << 22
     ibuf = np.zeros(cap, np.int32)
-    meta = np.zeros(64, np.int32)
+    meta = np.zeros(96, np.int32)
     jdst = np.zeros(1 << 18, np.int32)
     piv = np.zeros(1 << 12, np.int32)
     rc = fn(elems, circ.n_elems, circ.n_run, circ.n_start, cls.ctypes.data, an, ibuf.ctypes.data, cap, meta.ctypes.data,
@@ -72,6 +72,11 @@ def team_plan(circ, an=2):
     for k, o, ln in zip(["xlptr", "xlop", "flptr", "flop", "blptr", "blop"], meta[52:58],
                         [p["nXlev"] + 1, 2 * (p["n"] + p["nU"] + p["nDFop"]), p["nFlev"] + 1, 0, p["nBlev"] + 1, 2 * p["nDBop"]]):
         p[k] = ibuf[int(o):int(o) + ln].copy()
+    for key, (ns, o_seg, o_ops) in {"x": meta[59:62], "b": meta[62:65]}.items():
+        seg = ibuf[int(o_seg):int(o_seg) + 2 * int(ns)].reshape(-1, 2)
+        p[key + "seg"] = seg.copy()
+        n_ops = max([int(off) + (int(c) * NARROW if c > 0 else -int(c)) for c, off in seg] + [0])
+        p[key + "sop"] = ibuf[int(o_ops):int(o_ops) + 2 * n_ops].copy()
     p["spre"] = ibuf[int(meta[58]):int(meta[58]) + p["nJ"]].copy()
     p["scon"] = ibuf[int(meta[12]):int(meta[12]) + int(p["sptr"][-1])].copy()
     p["aptr"] = ibuf[int(meta[9]):int(meta[9]) + p["nSlotA"] + 1].copy()  # indexed by ELL slot (padding slots: empty lists)
@@ -161,6 +166,32 @@ def run_direct(p, vals, rhs):
         else:
             y[w0] = y[w0] - xi * sv[w1]
     return x
+
+
+NARROW, OP_NOP = 4, 0x20000000
+
+
+def levels_of_segments(seg, sop):
+    """The segmented form the kernel walks (seg_walk): runs of narrow levels padded to NARROW slots, wide levels plain."""
+    levels = []
+    for cnt, off in seg:
+        cnt, off = int(cnt), int(off)
+        if cnt < 0:
+            levels.append([(int(sop[2 * o]), int(sop[2 * o + 1])) for o in range(off, off - cnt)])
+        else:
+            for j in range(cnt):
+                ops = [(int(sop[2 * o]), int(sop[2 * o + 1])) for o in range(off + j * NARROW, off + (j + 1) * NARROW)]
+                levels.append([w for w in ops if not (w[1] >= 0 and (w[1] & OP_NOP))])
+    return levels
+
+
+def test_segmented_schedules_are_the_level_schedules():
+    for which in ("inverter258", "inverter40", "ladder64"):
+        p = team_plan(nl.load(CIRCUITS[which]()))
+        for key, lp, lo in (("x", "xlptr", "xlop"), ("b", "blptr", "blop")):
+            want = [[(int(p[lo][2 * o]), int(p[lo][2 * o + 1])) for o in range(p[lp][L], p[lp][L + 1])] for L in range(len(p[lp]) - 1)]
+            assert levels_of_segments(p[key + "seg"], p[key + "sop"]) == want, (which, key)
+            assert all(len(lv) > 0 for lv in want)
 
 
 def run_levels(p, vals, rhs, rng):
