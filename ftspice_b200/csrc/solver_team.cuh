@@ -698,6 +698,7 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
     auto is_cur = [&](int j, int) -> bool { return ((clsmask >> j) & 1u) != 0u; };
     const double dnv = (double)M.nv, dni = (double)M.ni, rnv = 1.0 / dnv, rni = 1.0 / dni;
     const bool has_ovf = P.nSlotA > W * (n + 1);
+    const int long_row = RC > 0 ? -1 : P.longRow; // generic Newton loop: the row whose overflow entries the team sums together
     double thr_v = 0.0, thr_i = 0.0; // RC > 0: the convergence tests as thresholds on the class sums of squares
     if constexpr (RC > 0) {
         thr_v = Ops::norm_threshold(dnv, rnv, 1e-6);
@@ -1092,9 +1093,28 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
                 sin_ = Ops::div_count(sqrt(qi), dni, rni);
                 __syncwarp();
                 flags = Ops::eval_nl(M, x, val, l, it_on);
-                double fv = 0.0, fi = 0.0;
+                double fv = 0.0, fi = 0.0, ax_long = 0.0;
+                const int nbad = flags & 0xfffff;
+                auto row_tail = [&](int row, double axv, bool cur) { // + H g - b, squared into the row's class sum
+                    double hg = 0.0;
+                    if (!linear && row < n) {
+                        int own_bad = 0;
+                        const int f0 = __ldg(&M.f_nl.ptr[row]), f1 = __ldg(&M.f_nl.ptr[row + 1]);
+                        for (int c = f0; c < f1; ++c) {
+                            const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
+                            const double v = val[wd & ~CON_NEG];
+                            own_bad += isfinite(v) ? 0 : 1;
+                            hg += (wd & CON_NEG) ? -v : v;
+                        }
+                        if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
+                    }
+                    const double f = axv + hg - b[row];
+                    if (cur)
+                        fi += f * f;
+                    else
+                        fv += f * f;
+                };
                 if (it_on) { // f = A x + H g - b (mna.rs:25-29) and its class norms (node_vec_norm.rs:12-33)
-                    const int nbad = flags & 0xfffff;
                     constexpr int RB = 3;
                     for (int j0 = 0; j0 < R; j0 += RB) {
                         int2 cols[RB];
@@ -1118,29 +1138,32 @@ __global__ void __launch_bounds__(32 * (RC > 0 ? TEAM_WARPS_ROWS : TEAM_WARPS_MA
 #pragma unroll
                         for (int u = 0; u < RB; ++u) {
                             const int row = row_[u];
+                            if (row == long_row) { // (summed by the whole team below)
+                                ax_long = ax[u];
+                                continue;
+                            }
                             if (has_ovf && row < n) {
                                 const int v0 = __ldg(&P.ovfptr[row]), v1 = __ldg(&P.ovfptr[row + 1]);
                                 for (int c = v0; c < v1; ++c) ax[u] = ax[u] + A[W * (n + 1) + c] * x[__ldg(&P.ovfcol[c])]; // long rows
                             }
-                            double hg = 0.0;
-                            if (!linear && row < n) {
-                                int own_bad = 0;
-                                const int f0 = __ldg(&M.f_nl.ptr[row]), f1 = __ldg(&M.f_nl.ptr[row + 1]);
-                                for (int c = f0; c < f1; ++c) {
-                                    const unsigned wd = (unsigned)__ldg(&M.f_nl.con[c]);
-                                    const double v = val[wd & ~CON_NEG];
-                                    own_bad += isfinite(v) ? 0 : 1;
-                                    hg += (wd & CON_NEG) ? -v : v;
-                                }
-                                if (nbad > own_bad) hg = __longlong_as_double(0x7ff8000000000000LL);
-                            }
-                            const double f = ax[u] + hg - b[row];
-                            if (is_cur(j0 + u, 0))
-                                fi += f * f;
-                            else
-                                fv += f * f;
+                            row_tail(row, ax[u], is_cur(j0 + u, 0));
                         }
                     }
+                }
+                if (long_row >= 0) { // the longest row (a supply rail: an entry per stage): the lanes of the team form the products,
+                                     // the sum runs over them in column order through shuffles — the same additions in the same
+                                     // order as one lane's loop, without its dependent L2 loads
+                    const int owner = long_row % G;
+                    const int v0 = __ldg(&P.ovfptr[long_row]), v1 = __ldg(&P.ovfptr[long_row + 1]);
+                    double acc = __shfl_sync(0xffffffffu, ax_long, owner, G);
+                    for (int c0 = v0; c0 < v1; c0 += G) {
+                        const int c = c0 + l;
+                        double pr = 0.0;
+                        if (it_on && c < v1) pr = A[W * (n + 1) + c] * x[__ldg(&P.ovfcol[c])];
+                        const int m = min(G, v1 - c0);
+                        for (int k = 0; k < m; ++k) acc = acc + __shfl_sync(0xffffffffu, pr, k, G);
+                    }
+                    if (it_on && l == owner) row_tail(long_row, acc, is_cur(long_row / G, 0));
                 }
                 Ops::sum2(fv, fi);
                 if (it_on) {

@@ -37,6 +37,7 @@ TeamPlan TeamPlanHost::view(const int *b) const
     p.ellcol = b + o_ellcol;
     p.ovfptr = b + o_ovfptr;
     p.ovfcol = b + o_ovfcol;
+    p.longRow = longRow;
     p.chain = chain;
     p.nFop = nFop;
     p.nBop = nBop;
@@ -207,6 +208,14 @@ bool build_team_plan(const Compiled &comp, int an, const std::vector<int> &pivse
     }
     out.ellW = W;
     out.nSlotA = (int)slot_con.size();
+    {
+        int best = 15;
+        for (int r = 0; r < n; ++r)
+            if (ovfptr[r + 1] - ovfptr[r] > best) {
+                best = ovfptr[r + 1] - ovfptr[r];
+                out.longRow = r;
+            }
+    }
 
     // ---- J: static entries in J_full order, then the fill-in of this pivot sequence ----
     const GatherOff &jf = mo.J_full;

@@ -47,6 +47,7 @@ struct TeamPlan {
     const int *ellcol;      // [n + 1][2] columns of the row's ELL entries, 16 bits each
     const int *ovfptr;      // [n + 1]
     const int *ovfcol;      // [n_ovf]
+    int longRow;            // the row with the most overflow entries if it has at least 16 (a supply rail), else -1
     // ---- substitutions as single-lane op streams (one lane of a team walks them; the values they need are staged
     //      through shared memory in chunks of TEAM_CHUNK by all lanes of the team).  Value indices address the factors
     //      array followed by the reciprocal pivots (index S + k).
@@ -107,7 +108,7 @@ struct TeamPlanHost {
     std::vector<int> ibuf;
     int o_arow = 0, o_acol = 0, o_aptr = 0, o_acon = 0, o_sptr = 0, o_scon = 0, o_spre = 0, o_pivrow = 0, o_pive = 0, o_tptr = 0, o_tgt = 0,
         o_tgtr = 0, o_uptr = 0, o_updm = 0, o_updds = 0, o_bptr = 0, o_bwde = 0, o_bwdr = 0;
-    int ellW = 0, nSlotA = 0, o_ellcol = 0, o_ovfptr = 0, o_ovfcol = 0;
+    int ellW = 0, nSlotA = 0, o_ellcol = 0, o_ovfptr = 0, o_ovfcol = 0, longRow = -1;
     int chain = 0, nFop = 0, nBop = 0, nFchunk = 0, nBchunk = 0, o_fop = 0, o_fvidx = 0, o_fchunk = 0, o_bop = 0, o_bvidx = 0,
         o_bchunk = 0;
     int nEarly = 0, nXop = 0, nDFop = 0, nDBop = 0, o_early = 0, o_xop = 0, o_dfop = 0, o_dbop = 0;
