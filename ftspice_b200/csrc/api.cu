@@ -1708,6 +1708,21 @@ int ftsb_get_counters(ftsb_circuit *c, ftsb_counters *out)
     return 0;
 }
 
+// diagnostics (not part of include/ftsb.h): why the structure-exploiting warp kernel handed instances to the dense kernels in the
+// last launch: out[0] pivot column with no usable candidate (zero-only / non-finite), out[1] fill-in pool exhausted, out[2]
+// non-finite solution component
+extern "C" int ftsb_debug_why(ftsb_circuit *c, int64_t *out)
+{
+    if (!c || !out) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -2;
+    unsigned long long h[CN_COUNT];
+    if (cudaMemcpyAsync(h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return -2;
+    for (int k = 0; k < 3; ++k) out[k] = (int64_t)((h[CN_WHY] >> (20 * k)) & 0xfffffull);
+    return 0;
+}
+
 int64_t ftsb_launch_count(const ftsb_circuit *c) { return c ? c->launches : 0; }
 const char *ftsb_last_variant(const ftsb_circuit *c) { return c ? c->variant.c_str() : ""; }
 

@@ -19,4 +19,10 @@ for rep in range(3):
     r = be.run_op()
     dt = time.perf_counter() - t0
     c = be.counters()
+    import ctypes as ct
+    from ftspice_b200 import capi
+    why = (ct.c_int64 * 3)()
+    capi.lib().ftsb_debug_why.argtypes = [ct.c_void_p, ct.c_void_p]
+    capi.lib().ftsb_debug_why(be.h, why)
+    c["why_pivot_fill_nonfinite"] = list(why)
     print(json.dumps({"instances": B, "seconds": dt, "ok": int((r.status == 0).sum()), "iters_mean": float(r.n_iters.mean()), "variant": be.variant, "counters": c}))
