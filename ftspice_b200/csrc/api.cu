@@ -815,7 +815,7 @@ int plan_team(ftsb_circuit *c, int an, long long batch, TeamLaunch &tl)
         TeamKernelFn fn = (mo.n + g - 1) / g <= 32 ? team_kernel(g, place, ph.ellW) : nullptr; // rows per lane fit a 32-bit class mask
         // linear circuit, rows per lane among the instantiated counts: registers instead of shared-memory round trips
         int rows = 0;
-        if (linear && ph.chain && g == TEAM_CHUNK && (place & 2) == 0 && c->team_rows && (mo.n + g - 1) / g <= 32) {
+        if (linear && ph.chain && g == 8 && (place & 2) == 0 && c->team_rows && (mo.n + g - 1) / g <= 32) {
             TeamKernelFn fr = team_kernel_rows(g, place, ph.ellW, (mo.n + g - 1) / g);
             if (fr) {
                 fn = fr;

@@ -101,7 +101,7 @@ struct TeamPlan {
 constexpr int TEAM_NARROW = 4;
 constexpr int TEAM_OP_NOP = 0x20000000, TEAM_OP_FWD = 0x40000000;
 
-constexpr int TEAM_CHUNK = 8; // value slots per chunk: two chunks of staging per instance (128 bytes); teams of more lanes use the lane-parallel substitutions
+constexpr int TEAM_CHUNK = 16; // value slots per chunk: two chunks of staging per instance (256 bytes; measured on C4: 8 slots 68.4, 16 slots 72.1, 32 slots 58.2 M solve-points/s); teams of more lanes use the lane-parallel substitutions
 
 struct TeamPlanHost {
     int n = 0, nA = 0, S = 0, nJ = 0, nT = 0, nU = 0, nB = 0, nPre = 0;

@@ -12,7 +12,7 @@ from ftspice_b200 import netlist as nl
 
 from test_q9_isource import mid_netlist
 
-CHUNK = 8  # TEAM_CHUNK of team_plan.h
+CHUNK = 16  # TEAM_CHUNK of team_plan.h
 
 CIRCUITS = {
     "ladder64": lambda: nl.ladder_netlist(64, "SIN( 0.0 1.0 10M )", stop="40n", step="1n"),
