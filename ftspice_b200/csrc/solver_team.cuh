@@ -20,6 +20,12 @@
 //   * what is touched once per accepted step — C/L state, the ring of the last three accepted x, for linear circuits
 //     also the slot table and the factors — lives in a per-warp global scratch region with the same [index][team]
 //     layout (coalesced, L2 resident): 3.6 KB of shared memory per instance at n = 65.
+//   * LINEAR circuits with 3..12 rows per lane of 8 (template parameter RC; kern_team_rows*.cu) run a Newton loop with the rows
+//     at compile-time offsets, x / x_proposed in registers, the convergence tests as thresholds on the class sums of squares and
+//     the residual evaluated only in the iterations whose step test passes (see the loop and TeamOps::norm_threshold);
+//   * NONLINEAR circuits (factors in shared memory) eliminate and substitute along LEVEL SCHEDULES (team_plan.h) with all lanes
+//     of the team, keep the partial sums of the linear prefixes of their factor entries per attempt, and sum their longest
+//     residual row (a supply rail) with the whole team.
 // The solution-path arithmetic (assembly order, pivot rule, reciprocal scaling, separate multiply / subtract, damping,
 // state update, PLTE) is the one of the other families, operation for operation: outputs compare equal bit for bit
 // (tests/test_gpu_parity.py).  Reference: transient.rs:18-105, newtons_method.rs:19-89, gauss_lu.rs:3-54,
